@@ -1,0 +1,362 @@
+// logmel_capi.cu -- extern "C" boundary of liblogmel_b200.so (see include/logmel_b200.h).
+//
+// Host side only: plan construction (twiddles, banded filterbank rows), launch, and the
+// host-buffer pipeline.  No torch types, no ATen: plain pointers and sizes.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "logmel_kernel.cuh"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return LM_ERR_CUDA;
+}
+#define LM_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t _e = (call);                             \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
+    } while (0)
+
+constexpr int kSlots = 3;   // host pipeline depth
+
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    float* d_wave = nullptr;      size_t cap_wave = 0;     // floats
+    float* d_noise = nullptr;     size_t cap_noise = 0;
+    float* d_out = nullptr;       size_t cap_out = 0;
+    long long* d_off = nullptr;   int* d_len = nullptr;   lm_aug* d_aug = nullptr;
+    long long* h_off = nullptr;   // pinned
+    int cap_clips = 0;
+};
+
+}  // namespace
+
+struct lm_plan {
+    int device = 0;
+    int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
+    int tile_f = 0, n_tiles = 0, ns = 0, mel_nnz = 0, fb_nnz = 0;
+    int sm_count = 0, max_ctas = 0, use_tma = 1;
+    size_t smem_bytes = 0;
+    float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
+    // device constants
+    float* d_window = nullptr;
+    float2* d_tw = nullptr;
+    float2* d_utw = nullptr;
+    float* d_melw = nullptr;
+    int* d_meta = nullptr;
+    // host pipeline
+    HostSlot slots[kSlots];
+    bool slots_ready = false;
+    long long launches = 0;
+};
+
+namespace {
+
+int free_plan(lm_plan* p) {
+    if (!p) return LM_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_meta);
+    for (auto& s : p->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        cudaFree(s.d_wave); cudaFree(s.d_noise); cudaFree(s.d_out);
+        cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_aug);
+        if (s.h_off) cudaFreeHost(s.h_off);
+    }
+    delete p;
+    return LM_OK;
+}
+
+lm::KParams make_params(const lm_plan* p) {
+    lm::KParams k{};
+    k.T = p->T; k.hop = p->hop; k.frames = p->frames; k.n_mels = p->n_mels; k.n_tiles = p->n_tiles;
+    k.ns = p->ns; k.mel_nnz = p->mel_nnz; k.use_tma = p->use_tma;
+    k.db_mult = p->db_mult; k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
+    k.norm_eps = p->norm_eps;
+    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.melw = p->d_melw; k.mel_meta = p->d_meta;
+    return k;
+}
+
+int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
+           const lm_aug* aug, const float* noise, float* out_norm, float* out_db, float* out_melpow,
+           int32_t normalize, cudaStream_t stream) {
+    if (B == 0) return LM_OK;
+    lm::KParams k = make_params(p);
+    k.wave = wave; k.offset = reinterpret_cast<const long long*>(offset); k.length = length;
+    k.aug = aug; k.noise = noise; k.out_norm = out_norm; k.out_db = out_db; k.out_melpow = out_melpow;
+    k.B = B; k.normalize = normalize;
+    const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
+    const int grid = std::min<int>(B, cap);
+    if (p->n_fft == 2048)
+        lm::logmel_kernel<2048><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    else
+        lm::logmel_kernel<1024><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    LM_CUDA(cudaGetLastError());
+    ++p->launches;
+    return LM_OK;
+}
+
+int ensure_slots(lm_plan* p) {
+    if (p->slots_ready) return LM_OK;
+    for (auto& s : p->slots) LM_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    p->slots_ready = true;
+    return LM_OK;
+}
+
+template <class Tp>
+int grow(Tp** ptr, size_t* cap, size_t want) {
+    if (want <= *cap) return LM_OK;
+    if (*ptr) LM_CUDA(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    LM_CUDA(cudaMalloc(reinterpret_cast<void**>(ptr), want * sizeof(Tp)));
+    *cap = want;
+    return LM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lm_abi_version(void) { return LM_ABI_VERSION; }
+
+const char* lm_strerror(int status) {
+    switch (status) {
+        case LM_OK: return "ok";
+        case LM_ERR_INVALID_ARG: return "invalid argument";
+        case LM_ERR_UNSUPPORTED: return "unsupported configuration (n_fft must be 1024 or 2048; hop even and <= n_fft/4; n_mels <= 256)";
+        case LM_ERR_FILTERBANK: return "filterbank support too wide for the on-chip table";
+        case LM_ERR_CUDA: return "CUDA runtime error (see lm_last_cuda_error)";
+        case LM_ERR_NO_DEVICE: return "no usable CUDA device (an sm_100 GPU is required; there is no CPU fallback)";
+        case LM_ERR_TOO_SHORT: return "target_len must exceed n_fft/2 (reflect padding)";
+        default: return "unknown status";
+    }
+}
+
+const char* lm_last_cuda_error(void) { return g_cuda_err; }
+
+int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
+    if (!cfg || !out_plan || !cfg->window || !cfg->fb) return LM_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    if (cfg->n_fft != 2048 && cfg->n_fft != 1024) return LM_ERR_UNSUPPORTED;
+    if (cfg->hop < 2 || (cfg->hop & 1) || cfg->hop > cfg->n_fft / 4) return LM_ERR_UNSUPPORTED;
+    if (cfg->n_mels < 1 || cfg->n_mels > 256) return LM_ERR_UNSUPPORTED;
+    if (cfg->target_len <= cfg->n_fft / 2) return LM_ERR_TOO_SHORT;
+    if (!(cfg->amin > 0.f)) return LM_ERR_INVALID_ARG;
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return LM_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop{};
+    LM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return LM_ERR_NO_DEVICE;   // the fatbin holds sm_100a code only
+    LM_CUDA(cudaSetDevice(device));
+
+    lm_plan* p = new (std::nothrow) lm_plan();
+    if (!p) return LM_ERR_INVALID_ARG;
+    p->device = device;
+    p->n_fft = cfg->n_fft; p->hop = cfg->hop; p->n_mels = cfg->n_mels; p->T = cfg->target_len;
+    p->n_freqs = cfg->n_fft / 2 + 1;
+    p->frames = 1 + cfg->target_len / cfg->hop;
+    p->tile_f = (cfg->n_fft == 2048) ? lm::Geo<2048>::TILE_F : lm::Geo<1024>::TILE_F;
+    p->n_tiles = (p->frames + p->tile_f - 1) / p->tile_f;
+    p->ns = (((p->tile_f - 1) * p->hop + p->n_fft) + 3) & ~3;
+    p->db_mult = cfg->db_multiplier; p->amin = cfg->amin; p->db_offset = cfg->db_offset;
+    p->norm_eps = cfg->norm_eps;
+    p->floor_db = cfg->db_multiplier * log10f(cfg->amin) - cfg->db_offset;
+    p->sm_count = prop.multiProcessorCount;
+
+    // ---- banded filterbank rows (scaled by 1/4: the kernel produces 4 |X|^2) ---------------
+    std::vector<float> melw;
+    std::vector<int> meta(3 * static_cast<size_t>(p->n_mels), 0);
+    int nnz = 0;
+    for (int m = 0; m < p->n_mels; ++m) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < p->n_freqs; ++k) {
+            if (cfg->fb[static_cast<size_t>(k) * p->n_mels + m] != 0.0f) {
+                if (lo < 0) lo = k;
+                hi = k;
+                ++nnz;
+            }
+        }
+        meta[m] = lo < 0 ? 0 : lo;
+        meta[p->n_mels + m] = lo < 0 ? 0 : hi - lo + 1;
+        meta[2 * p->n_mels + m] = static_cast<int>(melw.size());
+        for (int k = lo; lo >= 0 && k <= hi; ++k)
+            melw.push_back(0.25f * cfg->fb[static_cast<size_t>(k) * p->n_mels + m]);
+    }
+    p->fb_nnz = nnz;
+    while (melw.size() % 4) melw.push_back(0.0f);
+    if (melw.empty()) melw.assign(4, 0.0f);
+    if (melw.size() > static_cast<size_t>(lm::kMaxMelW)) { free_plan(p); return LM_ERR_FILTERBANK; }
+    p->mel_nnz = static_cast<int>(melw.size());
+
+    // ---- twiddles ---------------------------------------------------------------------------
+    std::vector<float2> tw(1024), utw(512);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = two_pi * static_cast<double>(k1 * n2) / 1024.0;
+            tw[k1 * 32 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
+        }
+    for (int k = 0; k < 512; ++k) {
+        const double a = two_pi * static_cast<double>(k) / 2048.0;
+        utw[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+    }
+
+    auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+        LM_CUDA(cudaMalloc(dst, bytes));
+        LM_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return LM_OK;
+    };
+    int rc = LM_OK;
+    if ((rc = up(reinterpret_cast<void**>(&p->d_window), cfg->window, sizeof(float) * p->n_fft)) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_tw), tw.data(), sizeof(float2) * tw.size())) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float) * melw.size())) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_meta), meta.data(), sizeof(int) * meta.size()))) {
+        free_plan(p);
+        return rc;
+    }
+
+    // ---- shared memory --------------------------------------------------------------------
+    cudaError_t e;
+    if (p->n_fft == 2048) {
+        p->smem_bytes = lm::Smem<2048>(p->ns, p->n_mels, p->mel_nnz).total;
+        e = cudaFuncSetAttribute(lm::logmel_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(p->smem_bytes));
+    } else {
+        p->smem_bytes = lm::Smem<1024>(p->ns, p->n_mels, p->mel_nnz).total;
+        e = cudaFuncSetAttribute(lm::logmel_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(p->smem_bytes));
+    }
+    if (e != cudaSuccess) { free_plan(p); return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
+    *out_plan = p;
+    return LM_OK;
+}
+
+int lm_plan_destroy(lm_plan* plan) { return free_plan(plan); }
+
+int lm_plan_frames(const lm_plan* plan) { return plan ? plan->frames : LM_ERR_INVALID_ARG; }
+
+int lm_plan_info(const lm_plan* plan, lm_info* info) {
+    if (!plan || !info) return LM_ERR_INVALID_ARG;
+    info->abi_version = LM_ABI_VERSION;
+    info->frames = plan->frames;
+    info->n_freqs = plan->n_freqs;
+    info->sm_count = plan->max_ctas > 0 ? plan->max_ctas : plan->sm_count;
+    info->threads_per_cta = lm::kThreads;
+    info->smem_bytes = static_cast<int32_t>(plan->smem_bytes);
+    info->fb_nnz = plan->fb_nnz;
+    info->tma_staging = plan->use_tma;
+    info->bytes_per_clip = 4LL * plan->T + 4LL * plan->n_mels * plan->frames;
+    return LM_OK;
+}
+
+int lm_plan_set(lm_plan* plan, const char* key, int value) {
+    if (!plan || !key) return LM_ERR_INVALID_ARG;
+    if (!strcmp(key, "tma")) { plan->use_tma = value ? 1 : 0; return LM_OK; }
+    if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
+    return LM_ERR_INVALID_ARG;
+}
+
+int64_t lm_plan_launch_count(const lm_plan* plan) { return plan ? plan->launches : 0; }
+
+int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
+               const lm_aug* aug, const float* noise, float* out_norm, float* out_db, float* out_melpow,
+               int32_t normalize, void* cuda_stream) {
+    if (!plan || B < 0) return LM_ERR_INVALID_ARG;
+    if (B == 0) return LM_OK;
+    if (!wave || !offset || !length || !out_norm) return LM_ERR_INVALID_ARG;
+    int dev = -1;
+    LM_CUDA(cudaGetDevice(&dev));
+    if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
+    const int rc = launch(plan, wave, offset, length, B, aug, noise, out_norm, out_db, out_melpow, normalize,
+                          static_cast<cudaStream_t>(cuda_stream));
+    if (dev != plan->device) cudaSetDevice(dev);
+    return rc;
+}
+
+int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, const int64_t* offset,
+                    const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
+                    int32_t normalize) {
+    if (!plan || B < 0 || total_samples < 0) return LM_ERR_INVALID_ARG;
+    if (B == 0) return LM_OK;
+    if (!wave || !offset || !length || !out) return LM_ERR_INVALID_ARG;
+    for (int i = 0; i < B; ++i)
+        if (length[i] < 0 || offset[i] < 0 || offset[i] + length[i] > total_samples) return LM_ERR_INVALID_ARG;
+    int dev = -1;
+    LM_CUDA(cudaGetDevice(&dev));
+    LM_CUDA(cudaSetDevice(plan->device));
+    int rc = ensure_slots(plan);
+    if (rc) return rc;
+
+    const size_t clip_elems = static_cast<size_t>(plan->n_mels) * plan->frames;
+    // chunk so that a few chunks are in flight: ~64 MB of waveform, at least 2 SM-waves of clips
+    const int chunk = std::max(1, std::min<int>(B, std::max(2 * plan->sm_count,
+                                                            static_cast<int>((64u << 20) / (4u * static_cast<size_t>(plan->T))))));
+    int slot_i = 0;
+    for (int c0 = 0; c0 < B && rc == LM_OK; c0 += chunk, slot_i = (slot_i + 1) % kSlots) {
+        const int n = std::min(chunk, B - c0);
+        HostSlot& s = plan->slots[slot_i];
+        if ((rc = cudaStreamSynchronize(s.stream) == cudaSuccess ? LM_OK : cuda_fail(cudaGetLastError(), "slot sync"))) break;
+        int64_t lo = INT64_MAX, hi = 0;
+        for (int i = c0; i < c0 + n; ++i) {
+            if (length[i] == 0) continue;
+            lo = std::min(lo, offset[i]);
+            hi = std::max(hi, offset[i] + length[i]);
+        }
+        if (lo == INT64_MAX) { lo = 0; hi = 0; }
+        lo &= ~int64_t(3);   // keep 16-byte alignment of clip starts (TMA staging path)
+        const size_t n_wave = static_cast<size_t>(hi - lo);
+        if (n > s.cap_clips) {
+            cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_aug);
+            if (s.h_off) cudaFreeHost(s.h_off);
+            s.d_off = nullptr; s.d_len = nullptr; s.d_aug = nullptr; s.h_off = nullptr; s.cap_clips = 0;
+            if (cudaMalloc(&s.d_off, sizeof(long long) * n) != cudaSuccess ||
+                cudaMalloc(&s.d_len, sizeof(int) * n) != cudaSuccess ||
+                cudaMalloc(&s.d_aug, sizeof(lm_aug) * n) != cudaSuccess ||
+                cudaMallocHost(&s.h_off, sizeof(long long) * n) != cudaSuccess) {
+                rc = cuda_fail(cudaGetLastError(), "slot metadata alloc");
+                break;
+            }
+            s.cap_clips = n;
+        }
+        if ((rc = grow(&s.d_wave, &s.cap_wave, std::max<size_t>(n_wave + 4, 16)))) break;
+        if ((rc = grow(&s.d_out, &s.cap_out, clip_elems * n))) break;
+        if (noise && (rc = grow(&s.d_noise, &s.cap_noise, static_cast<size_t>(plan->T) * n))) break;
+        for (int i = 0; i < n; ++i) s.h_off[i] = length[c0 + i] ? offset[c0 + i] - lo : 0;
+
+        cudaError_t e = cudaSuccess;
+        if (n_wave) e = cudaMemcpyAsync(s.d_wave, wave + lo, sizeof(float) * n_wave, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_off, s.h_off, sizeof(long long) * n, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_len, length + c0, sizeof(int) * n, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess && aug) e = cudaMemcpyAsync(s.d_aug, aug + c0, sizeof(lm_aug) * n, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess && noise)
+            e = cudaMemcpyAsync(s.d_noise, noise + static_cast<size_t>(c0) * plan->T, sizeof(float) * plan->T * n,
+                                cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
+        rc = launch(plan, s.d_wave, reinterpret_cast<const int64_t*>(s.d_off), s.d_len, n, aug ? s.d_aug : nullptr,
+                    noise ? s.d_noise : nullptr, s.d_out, nullptr, nullptr, normalize, s.stream);
+        if (rc) break;
+        e = cudaMemcpyAsync(out + clip_elems * c0, s.d_out, sizeof(float) * clip_elems * n, cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }
+    }
+    for (auto& s : plan->slots) {
+        const cudaError_t e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess && rc == LM_OK) rc = cuda_fail(e, "pipeline drain");
+    }
+    cudaSetDevice(dev);
+    return rc;
+}
+
+}  // extern "C"
