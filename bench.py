@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples = []          # (t, sm_mhz, reasons bitmask, util)
         self.marks = []            # (t_begin, t_end) of timed regions
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
         if not self.ok:
             return
         nv = self.nv
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
 
     def summary(self) -> dict:
         if not self.ok or not self.samples:

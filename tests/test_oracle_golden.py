@@ -16,7 +16,7 @@ NORM_ATOL = 2e-4
 
 
 def rel_err(x, ref):
-    floor = 1e-6 * np.abs(ref).max()
+    floor = max(1e-6 * np.abs(ref).max(), 1e-30)
     return np.abs(x - ref) / np.maximum(np.abs(ref), floor)
 
 
