@@ -43,7 +43,7 @@ struct HostSlot {
 struct lm_plan {
     int device = 0;
     int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
-    int tile_f = 0, n_tiles = 0, ns = 0, mel_nnz = 0, fb_nnz = 0;
+    int tile_f = 0, n_tiles = 0, ns = 0, n_dk = 0, fb_nnz = 0;
     int sm_count = 0, max_ctas = 0, use_tma = 1;
     size_t smem_bytes = 0;
     float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
@@ -51,8 +51,8 @@ struct lm_plan {
     float* d_window = nullptr;
     float2* d_tw = nullptr;
     float2* d_utw = nullptr;
-    float* d_melw = nullptr;
-    int* d_meta = nullptr;
+    float4* d_melw = nullptr;
+    lm::MelTable* d_tab = nullptr;
     // host pipeline
     HostSlot slots[kSlots];
     bool slots_ready = false;
@@ -64,7 +64,7 @@ namespace {
 int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_meta);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -78,10 +78,11 @@ int free_plan(lm_plan* p) {
 lm::KParams make_params(const lm_plan* p) {
     lm::KParams k{};
     k.T = p->T; k.hop = p->hop; k.frames = p->frames; k.n_mels = p->n_mels; k.n_tiles = p->n_tiles;
-    k.ns = p->ns; k.mel_nnz = p->mel_nnz; k.use_tma = p->use_tma;
-    k.db_mult = p->db_mult; k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
+    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma;
+    k.db_scale = static_cast<float>(static_cast<double>(p->db_mult) * 0.30102999566398119521);
+    k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
     k.norm_eps = p->norm_eps;
-    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.melw = p->d_melw; k.mel_meta = p->d_meta;
+    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.melw = p->d_melw; k.mel_table = p->d_tab;
     return k;
 }
 
@@ -175,30 +176,61 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     p->floor_db = cfg->db_multiplier * log10f(cfg->amin) - cfg->db_offset;
     p->sm_count = prop.multiProcessorCount;
 
-    // ---- banded filterbank rows (scaled by 1/4: the kernel produces 4 |X|^2) ---------------
-    std::vector<float> melw;
-    std::vector<int> meta(3 * static_cast<size_t>(p->n_mels), 0);
+    // ---- banded filterbank as mma.sync B fragments (scaled by 1/4: the kernel produces 4 |X|^2) ----
+    // Mel tile mt = filters [8mt, 8mt+8).  Its band starts at kb (first non-zero bin, rounded down to
+    // 4) and is walked in steps of 16 bins.  For step d, lane (g = lane/4, tg = lane%4) holds
+    // fb[kb + 16d + 4tg + {0,1,2,3}][8mt + g] -- the k-permutation the kernel's LDS.128 A loads use.
+    const int n_mt = (p->n_mels + 7) / 8;
+    lm::MelTable tab{};
+    std::vector<float4> melw;
     int nnz = 0;
-    for (int m = 0; m < p->n_mels; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < p->n_freqs; ++k) {
-            if (cfg->fb[static_cast<size_t>(k) * p->n_mels + m] != 0.0f) {
-                if (lo < 0) lo = k;
-                hi = k;
-                ++nnz;
-            }
-        }
-        meta[m] = lo < 0 ? 0 : lo;
-        meta[p->n_mels + m] = lo < 0 ? 0 : hi - lo + 1;
-        meta[2 * p->n_mels + m] = static_cast<int>(melw.size());
-        for (int k = lo; lo >= 0 && k <= hi; ++k)
-            melw.push_back(0.25f * cfg->fb[static_cast<size_t>(k) * p->n_mels + m]);
-    }
+    for (int k = 0; k < p->n_freqs; ++k)
+        for (int m = 0; m < p->n_mels; ++m) nnz += cfg->fb[static_cast<size_t>(k) * p->n_mels + m] != 0.0f;
     p->fb_nnz = nnz;
-    while (melw.size() % 4) melw.push_back(0.0f);
-    if (melw.empty()) melw.assign(4, 0.0f);
-    if (melw.size() > static_cast<size_t>(lm::kMaxMelW)) { free_plan(p); return LM_ERR_FILTERBANK; }
-    p->mel_nnz = static_cast<int>(melw.size());
+    auto fbv = [&](int k, int m) -> float {
+        return (k < p->n_freqs && m < p->n_mels) ? 0.25f * cfg->fb[static_cast<size_t>(k) * p->n_mels + m] : 0.0f;
+    };
+    const int row_cap = (p->n_fft == 2048) ? lm::kRowFloats : (lm::kRowFloats - lm::kPbOff);
+    for (int mt = 0; mt < n_mt; ++mt) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < p->n_freqs; ++k)
+            for (int g = 0; g < 8; ++g)
+                if (fbv(k, 8 * mt + g) != 0.0f) { if (lo < 0) lo = k; hi = k; }
+        int kb = 0, ndk = 0;
+        if (lo >= 0) { kb = lo & ~3; ndk = (hi + 1 - kb + 15) / 16; }
+        if (kb + 16 * ndk > row_cap) { free_plan(p); return LM_ERR_FILTERBANK; }
+        tab.kb[mt] = kb; tab.ndk[mt] = ndk; tab.off[mt] = static_cast<int>(melw.size() / 32);
+        for (int d = 0; d < ndk; ++d)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, tg = lane & 3, k0 = kb + 16 * d + 4 * tg, m = 8 * mt + g;
+                melw.push_back(make_float4(fbv(k0, m), fbv(k0 + 1, m), fbv(k0 + 2, m), fbv(k0 + 3, m)));
+            }
+    }
+    if (melw.empty()) melw.assign(32, make_float4(0.f, 0.f, 0.f, 0.f));
+    p->n_dk = static_cast<int>(melw.size() / 32);
+    if (p->n_dk > lm::kMaxDk) { free_plan(p); return LM_ERR_FILTERBANK; }
+    // longest-processing-time assignment of mel tiles to warps, balanced per scheduler (warp % 4)
+    {
+        for (auto& w : tab.warp_tile) { w[0] = -1; w[1] = -1; }
+        std::vector<int> order(n_mt);
+        for (int i = 0; i < n_mt; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return tab.ndk[a] > tab.ndk[b]; });
+        int load_w[lm::kWarps] = {0}, load_s[4] = {0, 0, 0, 0}, cnt_w[lm::kWarps] = {0};
+        for (int mt : order) {
+            int best = -1;
+            for (int w = 0; w < lm::kWarps; ++w) {
+                if (cnt_w[w] >= 2) continue;
+                if (best < 0) { best = w; continue; }
+                const int a = load_s[w & 3] * 64 + load_w[w] * 2 + cnt_w[w];
+                const int b = load_s[best & 3] * 64 + load_w[best] * 2 + cnt_w[best];
+                // fewest tiles first (spread), then lightest scheduler, then lightest warp
+                if (cnt_w[w] < cnt_w[best] || (cnt_w[w] == cnt_w[best] && a < b)) best = w;
+            }
+            tab.warp_tile[best][cnt_w[best]++] = mt;
+            load_w[best] += tab.ndk[mt] + 1;
+            load_s[best & 3] += tab.ndk[mt] + 1;
+        }
+    }
 
     // ---- twiddles ---------------------------------------------------------------------------
     std::vector<float2> tw(1024), utw(512);
@@ -222,8 +254,8 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     if ((rc = up(reinterpret_cast<void**>(&p->d_window), cfg->window, sizeof(float) * p->n_fft)) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tw), tw.data(), sizeof(float2) * tw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
-        (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float) * melw.size())) ||
-        (rc = up(reinterpret_cast<void**>(&p->d_meta), meta.data(), sizeof(int) * meta.size()))) {
+        (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float4) * melw.size())) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab)))) {
         free_plan(p);
         return rc;
     }
@@ -231,11 +263,11 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     // ---- shared memory --------------------------------------------------------------------
     cudaError_t e;
     if (p->n_fft == 2048) {
-        p->smem_bytes = lm::Smem<2048>(p->ns, p->n_mels, p->mel_nnz).total;
+        p->smem_bytes = lm::Smem<2048>(p->ns, p->n_dk).total;
         e = cudaFuncSetAttribute(lm::logmel_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(p->smem_bytes));
     } else {
-        p->smem_bytes = lm::Smem<1024>(p->ns, p->n_mels, p->mel_nnz).total;
+        p->smem_bytes = lm::Smem<1024>(p->ns, p->n_dk).total;
         e = cudaFuncSetAttribute(lm::logmel_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(p->smem_bytes));
     }

@@ -1,23 +1,27 @@
 // logmel_kernel.cuh -- the fused log-mel kernel for sm_100a (B200).
 //
-// One persistent CTA per SM (16 warps).  A CTA takes whole clips (blockIdx.x, += gridDim.x) and,
-// per clip, walks tiles of 16 frames (32 for n_fft = 1024):
+// One persistent CTA per SM (16 warps).  A CTA takes whole clips (blockIdx.x, += gridDim.x) and
+// walks a flat list of work items (clip, tile); a tile is 16 frames (32 for n_fft = 1024).
+// Per item:
 //
-//   stage   the tile's samples -> shared memory, once per sample although every sample feeds
-//           4 frames.  Interior tiles of un-augmented clips are one cp.async.bulk (TMA, 1-D)
-//           issued a tile ahead into the other buffer; edge tiles / augmented clips go through
-//           the gather path that does pad/crop (R/src/data/preprocessing.py:70-83), noise and
-//           roll (:85-93) and torch.stft's reflect padding as index arithmetic.
-//   frame   one warp = one frame.  x Hann, 2048 real -> 1024 complex points held as
+//   stage   (done one item AHEAD, into the other buffer) the tile's samples -> shared memory,
+//           once per sample although every sample feeds 4 frames.  The contiguous interior of
+//           a plain clip is one cp.async.bulk (TMA, 1-D) completing on an mbarrier; whatever
+//           is left -- torch.stft's reflect padding, zero padding, and whole tiles of augmented
+//           clips -- goes through the gather path that does pad/crop
+//           (R/src/data/preprocessing.py:70-83), noise and roll (:85-93) as index arithmetic.
+//   FFT     one warp = one frame.  x Hann, 2048 real -> 1024 complex points held as
 //           32 registers/lane; register radix-32 FFT over the lane-local index, twiddle,
-//           32x32 transpose through a private shared-memory scratch, second radix-32 FFT,
+//           32x32 transpose through the warp's shared-memory row, second radix-32 FFT,
 //           then the real-FFT untangle with the partner bin fetched by warp shuffle;
-//           |X|^2 lands in the scratch (never in HBM).
+//           4|X|^2 overwrites the warp's row (never HBM).
 //           (TA/functional/functional.py:123-145: torch.stft + abs().pow(2))
-//   mel+dB  sparse banded filterbank rows from shared memory, 10*log10(max(x, amin))
-//           (TA/transforms/_transforms.py:417, TA/functional/functional.py:390-391)
-//   flush   the [n_mels x 16] dB tile is written with the SpecAugment intervals applied
-//           (TA/functional/functional.py:939-953) and fp64 sum / sum-of-squares are kept.
+//   mel     [16 frames x bins] . [bins x 8 mels] per warp on the tensor cores:
+//           mma.sync m16n8k8 TF32 with both operands split hi+lo (3 MMAs per step, error
+//           ~2^-22), walking only the band of bins the 8 filters touch
+//           (TA/transforms/_transforms.py:417).  Epilogue in registers: 10*log10(max(x, amin))
+//           (TA/functional/functional.py:390-391), SpecAugment intervals (:939-953), store,
+//           fp64 sum / sum-of-squares.
 //   norm    when the clip is finished the same CTA re-reads its (L2-resident) dB block and
 //           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116).
 //
@@ -33,9 +37,18 @@ namespace lm {
 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kScrPitch = 36;                 // 32 + 4: rows 16 B aligned, LDS.128 conflict-free
-constexpr int kScrFloats = 32 * kScrPitch;    // 1152 >= 1025 power bins
-constexpr int kMaxMelW = 6144;                // filterbank non-zeros kept on chip
+constexpr int kScrPitch = 36;                 // transpose rows: 32 + 4 (16 B aligned, LDS.128 conflict-free)
+constexpr int kRowFloats = 1168;              // per-warp row: >= 32*36 and == 16 (mod 32) for the MMA loads
+constexpr int kPbOff = 528;                   // n_fft=1024: second frame's spectrum inside the row (== 16 mod 32)
+constexpr int kMaxMelTiles = 32;              // n_mels <= 256
+constexpr int kMaxDk = 96;                    // 16-bin steps of banded filterbank kept on chip (48 KB)
+
+struct MelTable {                             // lives in global memory, copied to shared
+    int kb[kMaxMelTiles];                     // first bin of the tile's band (multiple of 4)
+    int ndk[kMaxMelTiles];                    // 16-bin steps in the band
+    int off[kMaxMelTiles];                    // first step's index into melw (units of 32 float4)
+    int warp_tile[kWarps][2];                 // mel tiles owned by each warp (-1 = none)
+};
 
 struct KParams {
     // batch
@@ -52,18 +65,19 @@ struct KParams {
     // plan
     int T, hop, frames, n_mels, n_tiles;
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
-    int mel_nnz;     // floats in melw (padded to 4)
+    int n_dk;        // total 16-bin steps in melw
     int use_tma;
-    float db_mult, amin, db_offset, floor_db, norm_eps;
+    float db_scale;  // db_multiplier * log10(2): dB = db_scale * log2(x) - db_offset
+    float amin, db_offset, floor_db, norm_eps;
     const float* __restrict__ window;   // [NFFT]
     const float2* __restrict__ tw;      // [32*32]  W1024^(n2*k1) = (cos, -sin), index k1*32+n2
     const float2* __restrict__ utw;     // [512]    (cos, sin)(2 pi k / 2048)
-    const float* __restrict__ melw;     // concatenated filter rows, pre-scaled by 1/4
-    const int* __restrict__ mel_meta;   // [3*n_mels]: start bin, length, offset into melw
+    const float4* __restrict__ melw;    // [n_dk][32 lanes]: fb/4 in mma B-fragment order
+    const MelTable* __restrict__ mel_table;
 };
 
 // ---------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk copy (TMA) global -> shared
+// PTX helpers: mbarrier + 1-D bulk copy (TMA) global -> shared, TF32 mma
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -100,6 +114,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// D += A(16x8, row) * B(8x8, col), TF32 inputs (low 13 mantissa bits ignored), fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 -> N(0,1): throughput-mode noise when no host-drawn noise is supplied
@@ -125,7 +149,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 
 // ---------------------------------------------------------------------------------------
 // 1024-point complex FFT of one warp: lane n2 holds z[32*n1 + n2] in slot n1 on entry,
-// lane k1 holds Z[k1 + 32*k2] in slot k2 on exit.
+// lane k1 holds Z[k1 + 32*k2] in slot k2 on exit.  `scr` is the warp's private row.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_cfft1024(float (&xr)[32], float (&xi)[32], float* __restrict__ scr,
                                               const float2* __restrict__ tw, int lane) {
@@ -159,81 +183,98 @@ __device__ __forceinline__ void warp_cfft1024(float (&xr)[32], float (&xi)[32], 
     lm_fft32(xr, xi);
 }
 
-// mel rows + dB for one frame whose (4x) power spectrum is in P
-__device__ __forceinline__ void mel_db_frame(const KParams& p, const float* __restrict__ P,
-                                             const float* __restrict__ melw, const int* __restrict__ meta,
-                                             float* __restrict__ dbt, int pitch, int f_local, int lane,
-                                             size_t out_base /* clip*n_mels*frames + t */, bool write_pow) {
-    for (int m = lane; m < p.n_mels; m += 32) {
-        const int st = meta[m], ln = meta[p.n_mels + m], of = meta[2 * p.n_mels + m];
-        float acc = 0.0f;
-        for (int i = 0; i < ln; ++i) acc = fmaf(melw[of + i], P[st + i], acc);
-        const float db = (acc <= p.amin) ? p.floor_db : fmaf(p.db_mult, log10f(acc), -p.db_offset);
-        dbt[m * pitch + f_local] = db;
-        if (write_pow) p.out_melpow[out_base + static_cast<size_t>(m) * p.frames] = acc;
-    }
-}
-
 template <int NFFT>
 struct Geo {
     static constexpr int FPW = (NFFT == 2048) ? 1 : 2;   // frames per warp pass
     static constexpr int TILE_F = kWarps * FPW;
-    static constexpr int PITCH = TILE_F + 1;
+    static constexpr int MT = TILE_F / 16;               // 16-frame MMA row blocks per tile
 };
 
 // Shared-memory carve-up, shared by host (size) and device (pointers).
 template <int NFFT>
 struct Smem {
     static __host__ __device__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-    size_t o_bar, o_red, o_sbuf, o_scr, o_dbt, o_win, o_tw, o_utw, o_melw, o_meta, total;
-    __host__ __device__ Smem(int ns, int n_mels, int mel_nnz) {
+    size_t o_bar, o_red, o_tab, o_sbuf, o_scr, o_win, o_tw, o_utw, o_melw, total;
+    __host__ __device__ Smem(int ns, int n_dk) {
         size_t o = 0;
         o_bar = o; o += 16;
         o_red = o; o += sizeof(double) * 2 * kWarps + 16;
         o = align16(o);
+        o_tab = o; o += align16(sizeof(MelTable));
         o_sbuf = o; o += sizeof(float) * 2 * static_cast<size_t>(ns);
-        o_scr = o; o += sizeof(float) * kWarps * kScrFloats;
-        o_dbt = o; o += align16(sizeof(float) * static_cast<size_t>(n_mels) * Geo<NFFT>::PITCH);
+        o_scr = o; o += sizeof(float) * kWarps * kRowFloats;
         o_win = o; o += sizeof(float) * NFFT;
         o_tw = o; o += sizeof(float2) * 1024;
         o_utw = o; o += (NFFT == 2048) ? sizeof(float2) * 512 : 0;
-        o_melw = o; o += align16(sizeof(float) * static_cast<size_t>(mel_nnz));
-        o_meta = o; o += align16(sizeof(int) * 3 * static_cast<size_t>(n_mels));
+        o_melw = o; o += sizeof(float4) * 32 * static_cast<size_t>(n_dk);
         total = o;
     }
 };
+
+// Everything the staging and epilogue code needs to know about one clip (CTA-uniform).
+struct ClipCtx {
+    const float* src;    // first sample after the centre crop
+    const float* nz;     // host-drawn noise row or nullptr
+    uint64_t seed;
+    int lc;              // valid samples after pad/crop
+    int shift, f0, f1, t0, t1;
+    float nscale, gain;
+    bool plain;
+};
+
+__device__ __forceinline__ ClipCtx load_clip(const KParams& p, int clip) {
+    ClipCtx c;
+    const long long off = p.offset[clip];
+    const int len = p.length[clip];
+    const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
+    c.lc = len < p.T ? len : p.T;
+    c.src = p.wave + off + crop;
+    c.shift = 0; c.f0 = c.f1 = c.t0 = c.t1 = 0; c.nscale = 0.0f; c.gain = 1.0f; c.seed = 0;
+    if (p.aug != nullptr) {
+        const lm_aug a = p.aug[clip];
+        c.shift = a.shift; c.nscale = a.noise_scale; c.gain = a.gain;
+        c.f0 = a.f0; c.f1 = a.f1; c.t0 = a.t0; c.t1 = a.t1; c.seed = a.seed;
+    }
+    c.nz = (p.noise != nullptr && c.nscale != 0.0f) ? p.noise + static_cast<size_t>(clip) * p.T : nullptr;
+    c.plain = (c.shift == 0) && (c.nscale == 0.0f) && (c.gain == 1.0f);
+    return c;
+}
 
 template <int NFFT>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     using G = Geo<NFFT>;
     constexpr int TILE_F = G::TILE_F;
-    constexpr int PITCH = G::PITCH;
     constexpr int HALF = NFFT / 2;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const Smem<NFFT> L(p.ns, p.n_mels, p.mel_nnz);
+    const Smem<NFFT> L(p.ns, p.n_dk);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.o_bar);
     double* red = reinterpret_cast<double*>(smem_raw + L.o_red);
     float* bcast = reinterpret_cast<float*>(smem_raw + L.o_red + sizeof(double) * 2 * kWarps);
+    const MelTable* s_tab = reinterpret_cast<const MelTable*>(smem_raw + L.o_tab);
     float* sbuf = reinterpret_cast<float*>(smem_raw + L.o_sbuf);
     float* scr_all = reinterpret_cast<float*>(smem_raw + L.o_scr);
-    float* dbt = reinterpret_cast<float*>(smem_raw + L.o_dbt);
     float* s_win = reinterpret_cast<float*>(smem_raw + L.o_win);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw + L.o_tw);
     float2* s_utw = reinterpret_cast<float2*>(smem_raw + L.o_utw);
-    float* s_melw = reinterpret_cast<float*>(smem_raw + L.o_melw);
-    int* s_meta = reinterpret_cast<int*>(smem_raw + L.o_meta);
+    float4* s_melw = reinterpret_cast<float4*>(smem_raw + L.o_melw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* scr = scr_all + warp * kScrFloats;
+    float* scr = scr_all + warp * kRowFloats;
+
+    const int n_my = (p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    if (n_my <= 0) return;
+    const int n_items = n_my * p.n_tiles;
 
     // ---- constants -> shared memory, once per (persistent) CTA -----------------------------
     for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 1024; i += kThreads) s_tw[i] = p.tw[i];
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
-    for (int i = tid; i < p.mel_nnz; i += kThreads) s_melw[i] = p.melw[i];
-    for (int i = tid; i < 3 * p.n_mels; i += kThreads) s_meta[i] = p.mel_meta[i];
+    for (int i = tid; i < 32 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
+    for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
+        reinterpret_cast<int*>(smem_raw + L.o_tab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
+    for (int i = tid; i < kWarps * kRowFloats; i += kThreads) scr_all[i] = 0.0f;   // pad columns stay finite
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -241,254 +282,283 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     }
     __syncthreads();
 
-    uint32_t parity0 = 0, parity1 = 0;     // mbarrier phase per staging buffer (CTA-uniform)
-    bool pending0 = false, pending1 = false;
-
     const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
     const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
 
-#pragma unroll 1
-    for (int clip = blockIdx.x; clip < p.B; clip += gridDim.x) {
-        // ---- per-clip scalars (uniform) ---------------------------------------------------
-        const long long off = p.offset[clip];
-        const int len = p.length[clip];
-        const int crop = len > T ? (len - T) / 2 : 0;      // centre crop
-        const int lc = len < T ? len : T;                  // valid samples after pad/crop
-        const float* __restrict__ src = p.wave + off + crop;
-        int shift = 0, f0 = 0, f1 = 0, t0m = 0, t1m = 0;
-        float nscale = 0.0f, gain = 1.0f;
-        uint64_t seed = 0;
-        if (p.aug != nullptr) {
-            const lm_aug a = p.aug[clip];
-            shift = a.shift; nscale = a.noise_scale; gain = a.gain;
-            f0 = a.f0; f1 = a.f1; t0m = a.t0; t1m = a.t1; seed = a.seed;
-        }
-        const float* __restrict__ nz = (p.noise != nullptr && nscale != 0.0f)
-                                           ? p.noise + static_cast<size_t>(clip) * T : nullptr;
-        const bool plain = (shift == 0) && (nscale == 0.0f) && (gain == 1.0f);
-        float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
-        float* __restrict__ odb = p.out_db ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
-
-        double s_acc = 0.0, q_acc = 0.0;
-
-        auto tile_need = [&](int tile) {   // samples the tile's valid frames touch
-            const int tf = tile * TILE_F;
-            const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-            return (nf - 1) * hop + NFFT;
-        };
-        auto tile_contig = [&](int tile) { // all of them plain interior samples?
-            const int j0 = tile * TILE_F * hop - HALF;
-            const int need4 = (tile_need(tile) + 3) & ~3;
-            return plain && j0 >= 0 && (j0 + need4) <= lc;
-        };
-        auto tile_tma_ok = [&](int tile) {
-            if (!p.use_tma || !tile_contig(tile)) return false;
-            const int j0 = tile * TILE_F * hop - HALF;
-            return (reinterpret_cast<uintptr_t>(src + j0) & 15u) == 0;
-        };
-        auto issue_tma = [&](int tile, int buf) {  // one thread
-            const int j0 = tile * TILE_F * hop - HALF;
-            const uint32_t bytes = static_cast<uint32_t>(((tile_need(tile) + 3) & ~3) * 4);
+    // ---- staging of one item into buffer `buf` -------------------------------------------------
+    // bulk part: [e_lo, e_lo + cnt) of the tile is src[j0 + e_lo ...] verbatim (plain clips only)
+    auto bulk_range = [&](const ClipCtx& c, int tile_, int& e_lo, int& cnt) {
+        e_lo = 0; cnt = 0;
+        if (!p.use_tma || !c.plain) return;
+        const int tf = tile_ * TILE_F;
+        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+        const int need = (nf - 1) * hop + NFFT;
+        const int j0 = tf * hop - HALF;
+        const int lo = j0 < 0 ? -j0 : 0;
+        int hi = c.lc - j0;
+        if (hi > need) hi = need;
+        if (hi <= lo) return;
+        if ((reinterpret_cast<uintptr_t>(c.src + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
+        e_lo = lo;
+        cnt = (hi - lo) & ~3;
+    };
+    auto stage_bulk = [&](const ClipCtx& c, int tile_, int buf) -> bool {   // thread 0 issues; all agree
+        int e_lo, cnt;
+        bulk_range(c, tile_, e_lo, cnt);
+        if (cnt == 0) return false;
+        if (tid == 0) {
+            const int j0 = tile_ * TILE_F * hop - HALF;
             fence_proxy_async();
-            mbar_expect_tx(&mbar[buf], bytes);
-            bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns, src + j0, bytes, &mbar[buf]);
-        };
+            mbar_expect_tx(&mbar[buf], static_cast<uint32_t>(cnt) * 4u);
+            bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns + e_lo, c.src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u,
+                     &mbar[buf]);
+        }
+        return true;
+    };
+    auto stage_gather = [&](const ClipCtx& c, int tile_, int buf) {   // all threads
+        int e_lo, cnt;
+        bulk_range(c, tile_, e_lo, cnt);
+        const int tf = tile_ * TILE_F;
+        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+        const int need = (nf - 1) * hop + NFFT;
+        const int j0 = tf * hop - HALF;
+        float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
+        // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
+        // feed only frames >= `frames` and are zeroed
+        for (int e = tid; e < p.ns; e += kThreads) {
+            if (e >= e_lo && e < e_lo + cnt) continue;
+            int j = j0 + e;
+            if (j < 0) j = -j;
+            else if (j >= T) j = 2 * (T - 1) - j;
+            float v = 0.0f;
+            if (e < need && j >= 0 && j < T) {
+                int i = j - c.shift;               // torch.roll: out[j] = in[(j - shift) mod T]
+                if (i < 0) i += T;
+                else if (i >= T) i -= T;
+                if (i < c.lc) v = __ldg(c.src + i) * c.gain;
+                if (c.nscale != 0.0f) {
+                    const float z = c.nz ? __ldg(c.nz + i) : philox_normal(c.seed, static_cast<uint32_t>(i));
+                    v = fmaf(z, c.nscale, v);
+                }
+            }
+            sb[e] = v;
+        }
+    };
+
+    uint32_t parity0 = 0, parity1 = 0;     // mbarrier phase per staging buffer (CTA-uniform)
+    bool pending0 = false, pending1 = false;
+
+    int clip = blockIdx.x;
+    ClipCtx ctx = load_clip(p, clip);
+    pending0 = stage_bulk(ctx, 0, 0);
+    stage_gather(ctx, 0, 0);
+    ClipCtx nctx = ctx;
+    double s_acc = 0.0, q_acc = 0.0;
+    int tile = 0;
 
 #pragma unroll 1
-        for (int tile = 0; tile < p.n_tiles; ++tile) {
-            const int buf = tile & 1;
-            const int tf = tile * TILE_F;                  // first frame of the tile
-            const int j0 = tf * hop - HALF;                // first sample (reflect-padded domain)
-            float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
-            const int need = tile_need(tile);
+    for (int it = 0; it < n_items; ++it) {
+        const int buf = it & 1;
+        const int tf = tile * TILE_F;                  // first frame of the tile
+        const float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
+        if (buf ? pending1 : pending0) {
+            mbar_wait(&mbar[buf], buf ? parity1 : parity0);
+            if (buf) { parity1 ^= 1u; pending1 = false; } else { parity0 ^= 1u; pending0 = false; }
+        }
+        __syncthreads();   // (A) item staged (gather part written last iteration); rows free again
 
-            // ---- stage --------------------------------------------------------------------
-            if (tile_tma_ok(tile)) {
-                bool& pend = buf ? pending1 : pending0;
-                uint32_t& par = buf ? parity1 : parity0;
-                if (!pend && tid == 0) issue_tma(tile, buf);
-                mbar_wait(&mbar[buf], par);
-                par ^= 1u;
-                pend = false;
-            } else if (tile_contig(tile)) {
-                const float* __restrict__ g = src + j0;
-                if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-                    const int n4 = (need + 3) >> 2;
-                    for (int e = tid; e < n4; e += kThreads)
-                        reinterpret_cast<float4*>(sb)[e] = __ldg(reinterpret_cast<const float4*>(g) + e);
-                } else {
-                    for (int e = tid; e < need; e += kThreads) sb[e] = __ldg(g + e);
+        // ---- next item: TMA now, gather after the mel phase ---------------------------------------
+        const bool has_next = (it + 1 < n_items);
+        const bool next_same_clip = (tile + 1 < p.n_tiles);
+        const int ntile = next_same_clip ? tile + 1 : 0;
+        if (has_next) {
+            if (!next_same_clip) nctx = load_clip(p, clip + gridDim.x);
+            const bool issued = stage_bulk(nctx, ntile, buf ^ 1);
+            if (buf) pending0 = issued; else pending1 = issued;
+        }
+
+        // ---- FFT phase: one frame per warp -> 4|X|^2 in the warp's row -------------------------------
+        if (NFFT == 2048) {
+            const int t = tf + warp;
+            if (t < frames) {
+                float xr[32], xi[32];
+                const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
+                const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float2 v = s2[32 * n1 + lane];
+                    const float2 w = w2[32 * n1 + lane];
+                    xr[n1] = v.x * w.x;
+                    xi[n1] = v.y * w.y;
                 }
-            } else {
-                // gather: reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise
-                // (slots past `need` feed only frames >= `frames`; zero them so the two-frame
-                //  n_fft=1024 packing never mixes stale shared memory into a valid frame)
-                for (int e = tid; e < p.ns; e += kThreads) {
-                    int j = j0 + e;
-                    if (j < 0) j = -j;
-                    else if (j >= T) j = 2 * (T - 1) - j;
-                    float v = 0.0f;
-                    if (e < need && j >= 0 && j < T) {
-                        int i = j - shift;               // torch.roll: out[j] = in[(j - shift) mod T]
-                        if (i < 0) i += T;
-                        else if (i >= T) i -= T;
-                        if (i < lc) v = __ldg(src + i) * gain;
-                        if (nscale != 0.0f) {
-                            const float z = nz ? __ldg(nz + i) : philox_normal(seed, static_cast<uint32_t>(i));
-                            v = fmaf(z, nscale, v);
+                warp_cfft1024(xr, xi, scr, s_tw, lane);
+                // real-FFT untangle: pair (k, 1024-k), partner lane (32-lane)&31 via shuffle.  The row
+                // was last read inside warp_cfft1024 (followed by __syncwarp): the power spectrum goes
+                // straight into it, bin-major.
+                const int srcl = (32 - lane) & 31;
+                const float z16r = xr[16], z16i = xi[16];
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
+                    float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
+                    if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
+                    const float ar = xr[k2], ai = xi[k2];
+                    const float er = ar + br, ei = ai - bi, orr = ai + bi, oi = br - ar;
+                    const float2 cs = s_utw[lane + 32 * k2];
+                    const float tr = fmaf(cs.x, orr, cs.y * oi);
+                    const float ti = fmaf(cs.x, oi, -cs.y * orr);
+                    const float ur = er + tr, ui = ei + ti, vr = er - tr, vi = ei - ti;
+                    scr[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
+                    scr[1024 - lane - 32 * k2] = fmaf(vr, vr, vi * vi);
+                }
+                if (lane == 0) scr[512] = 4.0f * fmaf(z16r, z16r, z16i * z16i);
+            }
+        } else {
+            // n_fft = 1024: two frames per warp as one complex signal z = a + i b
+            const int ta = tf + 2 * warp;
+            if (ta < frames) {
+                float xr[32], xi[32];
+                const float* __restrict__ sa = sb + (2 * warp) * hop;
+                const float* __restrict__ sbb = sa + hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float w = s_win[32 * n1 + lane];
+                    xr[n1] = sa[32 * n1 + lane] * w;
+                    xi[n1] = sbb[32 * n1 + lane] * w;
+                }
+                warp_cfft1024(xr, xi, scr, s_tw, lane);
+                // A = Z[k], B = Z[1024-k]:  |Xa|^2 = |A + conj B|^2 / 4, |Xb|^2 = |A - conj B|^2 / 4
+                const int srcl = (32 - lane) & 31;
+                const float z16r = xr[16], z16i = xi[16];
+                float* Pa = scr;
+                float* Pb = scr + kPbOff;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
+                    float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
+                    if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
+                    const float ar = xr[k2], ai = xi[k2];
+                    const float ur = ar + br, ui = ai - bi, vr = ar - br, vi = ai + bi;
+                    Pa[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
+                    Pb[lane + 32 * k2] = fmaf(vr, vr, vi * vi);
+                }
+                if (lane == 0) {   // k = 512 pairs with itself: A = B
+                    Pa[512] = 4.0f * z16r * z16r;
+                    Pb[512] = 4.0f * z16i * z16i;
+                }
+            }
+        }
+        __syncthreads();   // (B) all power rows of the tile are in shared memory
+
+        // ---- mel phase: tensor cores, one 8-mel column block per warp ---------------------------------
+        {
+            const int g = lane >> 2, tg = lane & 3;
+            const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+            float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+            float* __restrict__ odb = p.out_db ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ omp = p.out_melpow ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+#pragma unroll 1
+            for (int slot = 0; slot < 2; ++slot) {
+                const int mt = s_tab->warp_tile[warp][slot];
+                if (mt < 0) break;
+                const int kb = s_tab->kb[mt], ndk = s_tab->ndk[mt];
+                const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 32 + lane;
+#pragma unroll 1
+                for (int mb = 0; mb < G::MT; ++mb) {
+                    if (mb * 16 >= nf) break;
+                    // frame row f of the tile lives in warp row f/FPW (+ kPbOff for the odd frame)
+                    const int fa = mb * 16 + g, fb_ = fa + 8;
+                    const float* __restrict__ ra =
+                        scr_all + (fa / G::FPW) * kRowFloats + (fa % G::FPW) * kPbOff + kb + 4 * tg;
+                    const float* __restrict__ rb =
+                        scr_all + (fb_ / G::FPW) * kRowFloats + (fb_ % G::FPW) * kPbOff + kb + 4 * tg;
+                    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+                    for (int d = 0; d < ndk; ++d) {
+                        const float4 pa = *reinterpret_cast<const float4*>(ra + 16 * d);
+                        const float4 pb = *reinterpret_cast<const float4*>(rb + 16 * d);
+                        const float4 w = wp[32 * d];
+                        const uint32_t ah0 = tf32_hi(pa.x), ah1 = tf32_hi(pa.y), ah2 = tf32_hi(pa.z), ah3 = tf32_hi(pa.w);
+                        const uint32_t bh0 = tf32_hi(pb.x), bh1 = tf32_hi(pb.y), bh2 = tf32_hi(pb.z), bh3 = tf32_hi(pb.w);
+                        const uint32_t wh0 = tf32_hi(w.x), wh1 = tf32_hi(w.y), wh2 = tf32_hi(w.z), wh3 = tf32_hi(w.w);
+                        // k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
+                        mma_tf32(acc0, ah0, bh0, ah1, bh1, wh0, wh1);
+                        mma_tf32(acc1, tf32_lo(pa.x, ah0), tf32_lo(pb.x, bh0), tf32_lo(pa.y, ah1), tf32_lo(pb.y, bh1), wh0, wh1);
+                        mma_tf32(acc2, ah0, bh0, ah1, bh1, tf32_lo(w.x, wh0), tf32_lo(w.y, wh1));
+                        mma_tf32(acc0, ah2, bh2, ah3, bh3, wh2, wh3);
+                        mma_tf32(acc1, tf32_lo(pa.z, ah2), tf32_lo(pb.z, bh2), tf32_lo(pa.w, ah3), tf32_lo(pb.w, bh3), wh2, wh3);
+                        mma_tf32(acc2, ah2, bh2, ah3, bh3, tf32_lo(w.z, wh2), tf32_lo(w.w, wh3));
+                    }
+                    // epilogue: c0:(frame g, mel 2tg) c1:(g, 2tg+1) c2:(g+8, 2tg) c3:(g+8, 2tg+1)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int f = mb * 16 + g + ((c & 2) ? 8 : 0);
+                        const int m = mt * 8 + 2 * tg + (c & 1);
+                        if (f < nf && m < n_mels) {
+                            const int t = tf + f;
+                            const float mp = acc0[c] + (acc1[c] + acc2[c]);
+                            float v = (mp <= p.amin) ? p.floor_db : fmaf(p.db_scale, __log2f(mp), -p.db_offset);
+                            if ((m >= ctx.f0 && m < ctx.f1) || (t >= ctx.t0 && t < ctx.t1)) v = 0.0f;
+                            const size_t o = static_cast<size_t>(m) * frames + t;
+                            out[o] = v;
+                            if (odb) odb[o] = v;
+                            if (omp) omp[o] = mp;
+                            const double dv = static_cast<double>(v);
+                            s_acc += dv;
+                            q_acc = fma(dv, dv, q_acc);
                         }
                     }
-                    sb[e] = v;
                 }
             }
-            __syncthreads();   // (A) tile staged; previous flush finished
-
-            // ---- prefetch the next tile with TMA while this one is computed ------------------
-            if (tile + 1 < p.n_tiles && tile_tma_ok(tile + 1)) {
-                if (tid == 0) issue_tma(tile + 1, buf ^ 1);
-                if (buf) pending0 = true; else pending1 = true;
-            }
-
-            // ---- frames ---------------------------------------------------------------------
-            if (NFFT == 2048) {
-                const int t = tf + warp;
-                if (t < frames) {
-                    float xr[32], xi[32];
-                    const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
-                    const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
-#pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        const float2 v = s2[32 * n1 + lane];
-                        const float2 w = w2[32 * n1 + lane];
-                        xr[n1] = v.x * w.x;
-                        xi[n1] = v.y * w.y;
-                    }
-                    warp_cfft1024(xr, xi, scr, s_tw, lane);
-                    // real-FFT untangle: pair (k, 1024-k), partner lane (32-lane)&31 via shuffle
-                    const int srcl = (32 - lane) & 31;
-                    const float z16r = xr[16], z16i = xi[16];
-                    // scr was last read inside warp_cfft1024 (followed by __syncwarp): the
-                    // (4x) power spectrum goes straight into it, bin-major.
-#pragma unroll
-                    for (int k2 = 0; k2 < 16; ++k2) {
-                        float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
-                        float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
-                        if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
-                        const float ar = xr[k2], ai = xi[k2];
-                        const float er = ar + br, ei = ai - bi, orr = ai + bi, oi = br - ar;
-                        const float2 cs = s_utw[lane + 32 * k2];
-                        const float tr = fmaf(cs.x, orr, cs.y * oi);
-                        const float ti = fmaf(cs.x, oi, -cs.y * orr);
-                        const float ur = er + tr, ui = ei + ti, vr = er - tr, vi = ei - ti;
-                        scr[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
-                        scr[1024 - lane - 32 * k2] = fmaf(vr, vr, vi * vi);
-                    }
-                    if (lane == 0) scr[512] = 4.0f * fmaf(z16r, z16r, z16i * z16i);
-                    __syncwarp();
-                    mel_db_frame(p, scr, s_melw, s_meta, dbt, PITCH, warp, lane,
-                                 static_cast<size_t>(clip) * clip_elems + t, p.out_melpow != nullptr);
-                    __syncwarp();
-                }
-            } else {
-                // n_fft = 1024: two frames per warp as one complex signal z = a + i b
-                const int ta = tf + 2 * warp;
-                if (ta < frames) {
-                    float xr[32], xi[32];
-                    const float* __restrict__ sa = sb + (2 * warp) * hop;
-                    const float* __restrict__ sbb = sa + hop;
-#pragma unroll
-                    for (int n1 = 0; n1 < 32; ++n1) {
-                        const float w = s_win[32 * n1 + lane];
-                        xr[n1] = sa[32 * n1 + lane] * w;
-                        xi[n1] = sbb[32 * n1 + lane] * w;
-                    }
-                    warp_cfft1024(xr, xi, scr, s_tw, lane);
-                    // A = Z[k], B = Z[1024-k]:  |Xa|^2 = |A + conj B|^2 / 4, |Xb|^2 = |A - conj B|^2 / 4
-                    const int srcl = (32 - lane) & 31;
-                    const float z16r = xr[16], z16i = xi[16];
-                    float* Pa = scr;
-                    float* Pb = scr + 576;   // 513 bins each
-#pragma unroll
-                    for (int k2 = 0; k2 < 16; ++k2) {
-                        float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
-                        float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
-                        if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
-                        const float ar = xr[k2], ai = xi[k2];
-                        const float ur = ar + br, ui = ai - bi, vr = ar - br, vi = ai + bi;
-                        Pa[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
-                        Pb[lane + 32 * k2] = fmaf(vr, vr, vi * vi);
-                    }
-                    if (lane == 0) {   // k = 512 pairs with itself: A = B
-                        Pa[512] = 4.0f * z16r * z16r;
-                        Pb[512] = 4.0f * z16i * z16i;
-                    }
-                    __syncwarp();
-                    mel_db_frame(p, Pa, s_melw, s_meta, dbt, PITCH, 2 * warp, lane,
-                                 static_cast<size_t>(clip) * clip_elems + ta, p.out_melpow != nullptr);
-                    if (ta + 1 < frames)
-                        mel_db_frame(p, Pb, s_melw, s_meta, dbt, PITCH, 2 * warp + 1, lane,
-                                     static_cast<size_t>(clip) * clip_elems + ta + 1, p.out_melpow != nullptr);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();   // (B) dB tile complete
-
-            // ---- flush: masks, store, statistics -----------------------------------------------
-            {
-                const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-                for (int idx = tid; idx < n_mels * TILE_F; idx += kThreads) {
-                    const int m = idx / TILE_F, f = idx - m * TILE_F;
-                    if (f < nf) {
-                        const int t = tf + f;
-                        float v = dbt[m * PITCH + f];
-                        if ((m >= f0 && m < f1) || (t >= t0m && t < t1m)) v = 0.0f;
-                        const size_t o = static_cast<size_t>(m) * frames + t;
-                        out[o] = v;
-                        if (odb) odb[o] = v;
-                        const double d = static_cast<double>(v);
-                        s_acc += d;
-                        q_acc = fma(d, d, q_acc);
-                    }
-                }
-            }
-        }   // tiles
-
-        // ---- per-clip normalisation ------------------------------------------------------------
-        if (p.normalize) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-                q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
-            }
-            if (lane == 0) { red[warp] = s_acc; red[kWarps + warp] = q_acc; }
-            __syncthreads();   // also orders every thread's dB stores before the re-read below
-            if (tid == 0) {
-                double s = 0.0, q = 0.0;
-                for (int w = 0; w < kWarps; ++w) { s += red[w]; q += red[kWarps + w]; }
-                const double n = static_cast<double>(clip_elems);
-                const double mean = s / n;
-                double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
-                if (!(var > 0.0)) var = 0.0;
-                bcast[0] = static_cast<float>(mean);
-                bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
-            }
-            __syncthreads();
-            const float mean = bcast[0], denom = bcast[1];
-            float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
-            const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
-            for (int i = tid; i < n4; i += kThreads) {
-                float4 v = __ldcg(o4 + i);
-                v.x = __fdiv_rn(v.x - mean, denom);
-                v.y = __fdiv_rn(v.y - mean, denom);
-                v.z = __fdiv_rn(v.z - mean, denom);
-                v.w = __fdiv_rn(v.w - mean, denom);
-                o4[i] = v;
-            }
-            for (int i = (n4 << 2) + tid; i < static_cast<int>(clip_elems); i += kThreads)
-                out[i] = __fdiv_rn(__ldcg(out + i) - mean, denom);
-            __syncthreads();   // red/bcast reused by the next clip
         }
-    }   // clips
+
+        // ---- gather part of the next item (its TMA part is already in flight) -----------------------------
+        if (has_next) stage_gather(nctx, ntile, buf ^ 1);
+
+        // ---- per-clip normalisation --------------------------------------------------------------------
+        if (!next_same_clip) {
+            if (p.normalize) {
+                float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+                    q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
+                }
+                if (lane == 0) { red[warp] = s_acc; red[kWarps + warp] = q_acc; }
+                __syncthreads();   // also orders every thread's dB stores before the re-read below
+                if (tid == 0) {
+                    double s = 0.0, q = 0.0;
+                    for (int w = 0; w < kWarps; ++w) { s += red[w]; q += red[kWarps + w]; }
+                    const double n = static_cast<double>(clip_elems);
+                    const double mean = s / n;
+                    double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
+                    if (!(var > 0.0)) var = 0.0;
+                    bcast[0] = static_cast<float>(mean);
+                    bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
+                }
+                __syncthreads();
+                const float mean = bcast[0], inv = 1.0f / bcast[1];
+                float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+                const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
+                for (int i = tid; i < n4; i += kThreads) {
+                    float4 v = __ldcg(o4 + i);
+                    v.x = (v.x - mean) * inv;
+                    v.y = (v.y - mean) * inv;
+                    v.z = (v.z - mean) * inv;
+                    v.w = (v.w - mean) * inv;
+                    o4[i] = v;
+                }
+                for (int i = (n4 << 2) + tid; i < static_cast<int>(clip_elems); i += kThreads)
+                    out[i] = (__ldcg(out + i) - mean) * inv;
+            }
+            s_acc = 0.0; q_acc = 0.0;
+            clip += gridDim.x;
+            ctx = nctx;
+            tile = 0;
+        } else {
+            tile += 1;
+        }
+    }
 }
 
 }  // namespace lm
