@@ -117,7 +117,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // D += A(16x8, row) * B(8x8, col), TF32 inputs (low 13 mantissa bits ignored), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -148,39 +148,42 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 1024-point complex FFT of one warp: lane n2 holds z[32*n1 + n2] in slot n1 on entry,
-// lane k1 holds Z[k1 + 32*k2] in slot k2 on exit.  `scr` is the warp's private row.
+// 1024-point complex FFT of one warp.  On entry lane n2 holds z[32*n1 + n2] in z[n1] (re, im packed
+// in one 64-bit register); on exit lane k1 holds Z[k1 + 32*k2] in (xr[k2], xi[k2]).
+// `scr` is the warp's private row.  First FFT: packed complex (FFMA2/FADD2); the transpose moves the
+// real and imaginary planes separately and its LDS.128 reads hand the second FFT register pairs of
+// neighbouring points, which is the layout its packed stages 1-4 want (see gen_fft.py).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_cfft1024(float (&xr)[32], float (&xi)[32], float* __restrict__ scr,
-                                              const float2* __restrict__ tw, int lane) {
-    lm_fft32(xr, xi);
+__device__ __forceinline__ void warp_cfft1024(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
+                                              float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
+    lm_fft32_aos(z);
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = tw[k1 * 32 + lane];   // (cos, -sin)
-        const float r = xr[k1], i = xi[k1];
-        xr[k1] = fmaf(r, w.x, -i * w.y);
-        xi[k1] = fmaf(r, w.y, i * w.x);
+        const float2 w = tw[k1 * 32 + lane];   // (cos, -sin): (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy)
+        z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-w.y, w.y), lm_mul2(z[k1], lm_bcast(w.x)));
     }
-    // 32x32 transpose, real plane then imaginary plane
+    lm_f2 pr[16], pi[16];
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = xr[k1];
+    for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 v = *reinterpret_cast<const float4*>(scr + lane * kScrPitch + 4 * q);
-        xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+        pr[2 * q] = lm_pack(v.x, v.y);
+        pr[2 * q + 1] = lm_pack(v.z, v.w);
     }
     __syncwarp();
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = xi[k1];
+    for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_hi(z[k1]);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 v = *reinterpret_cast<const float4*>(scr + lane * kScrPitch + 4 * q);
-        xi[4 * q] = v.x; xi[4 * q + 1] = v.y; xi[4 * q + 2] = v.z; xi[4 * q + 3] = v.w;
+        pi[2 * q] = lm_pack(v.x, v.y);
+        pi[2 * q + 1] = lm_pack(v.z, v.w);
     }
     __syncwarp();
-    lm_fft32(xr, xi);
+    lm_fft32_soa(pr, pi, xr, xi);
 }
 
 template <int NFFT>
@@ -194,12 +197,13 @@ struct Geo {
 template <int NFFT>
 struct Smem {
     static __host__ __device__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-    size_t o_bar, o_red, o_tab, o_sbuf, o_scr, o_win, o_tw, o_utw, o_melw, total;
+    size_t o_bar, o_red, o_ctx, o_tab, o_sbuf, o_scr, o_win, o_tw, o_utw, o_melw, total;
     __host__ __device__ Smem(int ns, int n_dk) {
         size_t o = 0;
         o_bar = o; o += 16;
         o_red = o; o += sizeof(double) * 2 * kWarps + 16;
         o = align16(o);
+        o_ctx = o; o += 2 * 64;                       // two ClipCtx slots
         o_tab = o; o += align16(sizeof(MelTable));
         o_sbuf = o; o += sizeof(float) * 2 * static_cast<size_t>(ns);
         o_scr = o; o += sizeof(float) * kWarps * kRowFloats;
@@ -211,7 +215,8 @@ struct Smem {
     }
 };
 
-// Everything the staging and epilogue code needs to know about one clip (CTA-uniform).
+// Everything the staging and epilogue code needs to know about one clip.  Two slots live in
+// shared memory (current / next clip) so that none of it occupies registers across the FFT phase.
 struct ClipCtx {
     const float* src;    // first sample after the centre crop
     const float* nz;     // host-drawn noise row or nullptr
@@ -219,25 +224,29 @@ struct ClipCtx {
     int lc;              // valid samples after pad/crop
     int shift, f0, f1, t0, t1;
     float nscale, gain;
-    bool plain;
+    int plain;
+    int pad_;
 };
+static_assert(sizeof(ClipCtx) <= 64, "ClipCtx slot size");
 
-__device__ __forceinline__ ClipCtx load_clip(const KParams& p, int clip) {
-    ClipCtx c;
+__device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* __restrict__ c) {
     const long long off = p.offset[clip];
     const int len = p.length[clip];
     const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
-    c.lc = len < p.T ? len : p.T;
-    c.src = p.wave + off + crop;
-    c.shift = 0; c.f0 = c.f1 = c.t0 = c.t1 = 0; c.nscale = 0.0f; c.gain = 1.0f; c.seed = 0;
+    c->lc = len < p.T ? len : p.T;
+    c->src = p.wave + off + crop;
+    int shift = 0, f0 = 0, f1 = 0, t0 = 0, t1 = 0;
+    float nscale = 0.0f, gain = 1.0f;
+    uint64_t seed = 0;
     if (p.aug != nullptr) {
         const lm_aug a = p.aug[clip];
-        c.shift = a.shift; c.nscale = a.noise_scale; c.gain = a.gain;
-        c.f0 = a.f0; c.f1 = a.f1; c.t0 = a.t0; c.t1 = a.t1; c.seed = a.seed;
+        shift = a.shift; nscale = a.noise_scale; gain = a.gain;
+        f0 = a.f0; f1 = a.f1; t0 = a.t0; t1 = a.t1; seed = a.seed;
     }
-    c.nz = (p.noise != nullptr && c.nscale != 0.0f) ? p.noise + static_cast<size_t>(clip) * p.T : nullptr;
-    c.plain = (c.shift == 0) && (c.nscale == 0.0f) && (c.gain == 1.0f);
-    return c;
+    c->shift = shift; c->f0 = f0; c->f1 = f1; c->t0 = t0; c->t1 = t1;
+    c->nscale = nscale; c->gain = gain; c->seed = seed;
+    c->nz = (p.noise != nullptr && nscale != 0.0f) ? p.noise + static_cast<size_t>(clip) * p.T : nullptr;
+    c->plain = (shift == 0) && (nscale == 0.0f) && (gain == 1.0f);
 }
 
 template <int NFFT>
@@ -251,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.o_bar);
     double* red = reinterpret_cast<double*>(smem_raw + L.o_red);
     float* bcast = reinterpret_cast<float*>(smem_raw + L.o_red + sizeof(double) * 2 * kWarps);
+    ClipCtx* s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L.o_ctx);
     const MelTable* s_tab = reinterpret_cast<const MelTable*>(smem_raw + L.o_tab);
     float* sbuf = reinterpret_cast<float*>(smem_raw + L.o_sbuf);
     float* scr_all = reinterpret_cast<float*>(smem_raw + L.o_scr);
@@ -287,22 +297,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     // ---- staging of one item into buffer `buf` -------------------------------------------------
     // bulk part: [e_lo, e_lo + cnt) of the tile is src[j0 + e_lo ...] verbatim (plain clips only)
-    auto bulk_range = [&](const ClipCtx& c, int tile_, int& e_lo, int& cnt) {
+    auto bulk_range = [&](const ClipCtx* __restrict__ c, int tile_, int& e_lo, int& cnt) {
         e_lo = 0; cnt = 0;
-        if (!p.use_tma || !c.plain) return;
+        if (!p.use_tma || !c->plain) return;
         const int tf = tile_ * TILE_F;
         const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
         const int need = (nf - 1) * hop + NFFT;
         const int j0 = tf * hop - HALF;
         const int lo = j0 < 0 ? -j0 : 0;
-        int hi = c.lc - j0;
+        int hi = c->lc - j0;
         if (hi > need) hi = need;
         if (hi <= lo) return;
-        if ((reinterpret_cast<uintptr_t>(c.src + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
+        if ((reinterpret_cast<uintptr_t>(c->src + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
         e_lo = lo;
         cnt = (hi - lo) & ~3;
     };
-    auto stage_bulk = [&](const ClipCtx& c, int tile_, int buf) -> bool {   // thread 0 issues; all agree
+    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_, int buf) -> bool {   // thread 0 issues; all agree
         int e_lo, cnt;
         bulk_range(c, tile_, e_lo, cnt);
         if (cnt == 0) return false;
@@ -310,14 +320,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             const int j0 = tile_ * TILE_F * hop - HALF;
             fence_proxy_async();
             mbar_expect_tx(&mbar[buf], static_cast<uint32_t>(cnt) * 4u);
-            bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns + e_lo, c.src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u,
+            bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u,
                      &mbar[buf]);
         }
         return true;
     };
-    auto stage_gather = [&](const ClipCtx& c, int tile_, int buf) {   // all threads
+    auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_, int buf) {   // all threads
+        const ClipCtx c = *cc;
         int e_lo, cnt;
-        bulk_range(c, tile_, e_lo, cnt);
+        bulk_range(cc, tile_, e_lo, cnt);
         const int tf = tile_ * TILE_F;
         const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
         const int need = (nf - 1) * hop + NFFT;
@@ -325,8 +336,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
         // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
         // feed only frames >= `frames` and are zeroed
-        for (int e = tid; e < p.ns; e += kThreads) {
-            if (e >= e_lo && e < e_lo + cnt) continue;
+        const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
+        for (int idx = tid; idx < rest; idx += kThreads) {
+            const int e = idx < e_lo ? idx : idx + cnt;
             int j = j0 + e;
             if (j < 0) j = -j;
             else if (j >= T) j = 2 * (T - 1) - j;
@@ -349,10 +361,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     bool pending0 = false, pending1 = false;
 
     int clip = blockIdx.x;
-    ClipCtx ctx = load_clip(p, clip);
-    pending0 = stage_bulk(ctx, 0, 0);
-    stage_gather(ctx, 0, 0);
-    ClipCtx nctx = ctx;
+    int cur = 0;                       // s_ctx[cur] = this clip, s_ctx[cur ^ 1] = the next one
+    if (tid == 0) load_clip(p, clip, &s_ctx[0]);
+    __syncthreads();
+    pending0 = stage_bulk(&s_ctx[0], 0, 0);
+    stage_gather(&s_ctx[0], 0, 0);
     double s_acc = 0.0, q_acc = 0.0;
     int tile = 0;
 
@@ -371,9 +384,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         const bool has_next = (it + 1 < n_items);
         const bool next_same_clip = (tile + 1 < p.n_tiles);
         const int ntile = next_same_clip ? tile + 1 : 0;
+        const int nslot = next_same_clip ? cur : (cur ^ 1);
+        if (has_next && !next_same_clip) {
+            // the next clip's slot is idle (its previous owner finished a whole clip ago); every
+            // thread needs it right now for the uniform TMA decision, so one warp-wide sync it is
+            if (tid == 0) load_clip(p, clip + gridDim.x, &s_ctx[nslot]);
+            __syncthreads();
+        }
         if (has_next) {
-            if (!next_same_clip) nctx = load_clip(p, clip + gridDim.x);
-            const bool issued = stage_bulk(nctx, ntile, buf ^ 1);
+            const bool issued = stage_bulk(&s_ctx[nslot], ntile, buf ^ 1);
             if (buf) pending0 = issued; else pending1 = issued;
         }
 
@@ -381,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         if (NFFT == 2048) {
             const int t = tf + warp;
             if (t < frames) {
+                lm_f2 z[32];
                 float xr[32], xi[32];
                 const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
@@ -388,45 +408,67 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const float2 v = s2[32 * n1 + lane];
                     const float2 w = w2[32 * n1 + lane];
-                    xr[n1] = v.x * w.x;
-                    xi[n1] = v.y * w.y;
+                    z[n1] = lm_mul2(lm_pack(v.x, v.y), lm_pack(w.x, w.y));
                 }
-                warp_cfft1024(xr, xi, scr, s_tw, lane);
-                // real-FFT untangle: pair (k, 1024-k), partner lane (32-lane)&31 via shuffle.  The row
-                // was last read inside warp_cfft1024 (followed by __syncwarp): the power spectrum goes
-                // straight into it, bin-major.
+                warp_cfft1024(z, xr, xi, scr, s_tw, lane);
+                // Real-FFT untangle.  Bin k = lane + 32*k2 pairs with 1024-k, which lives in lane
+                // (32-lane)&31 at slot 31-k2 (lane 0: slot (32-k2)&31) and comes over by warp shuffle.
+                // Two pairs per packed op: k2 = i (lo half) and k2 = i+16 (hi half), i = 0..7; their
+                // partners are the other lane's slots 31-i and 15-i, and the hi twiddle is the lo one
+                // turned by pi/2: (c, s)(k+512) = (-s, c)(k).  The row was last read inside
+                // warp_cfft1024 (followed by __syncwarp): 4|X|^2 goes straight into it, bin-major.
                 const int srcl = (32 - lane) & 31;
-                const float z16r = xr[16], z16i = xi[16];
+                const bool l0 = (lane == 0);
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
-                    float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
-                    if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
-                    const float ar = xr[k2], ai = xi[k2];
-                    const float er = ar + br, ei = ai - bi, orr = ai + bi, oi = br - ar;
-                    const float2 cs = s_utw[lane + 32 * k2];
-                    const float tr = fmaf(cs.x, orr, cs.y * oi);
-                    const float ti = fmaf(cs.x, oi, -cs.y * orr);
-                    const float ur = er + tr, ui = ei + ti, vr = er - tr, vi = ei - ti;
-                    scr[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
-                    scr[1024 - lane - 32 * k2] = fmaf(vr, vr, vi * vi);
+                for (int i = 0; i < 8; ++i) {
+                    const float s_lr = l0 ? xr[(32 - i) & 31] : xr[31 - i];
+                    const float s_li = l0 ? xi[(32 - i) & 31] : xi[31 - i];
+                    const float s_hr = l0 ? xr[(16 - i) & 31] : xr[15 - i];
+                    const float s_hi = l0 ? xi[(16 - i) & 31] : xi[15 - i];
+                    const float b_lr = __shfl_sync(0xffffffffu, s_lr, srcl);
+                    const float b_li = __shfl_sync(0xffffffffu, s_li, srcl);
+                    const float b_hr = __shfl_sync(0xffffffffu, s_hr, srcl);
+                    const float b_hi = __shfl_sync(0xffffffffu, s_hi, srcl);
+                    const lm_f2 Ar = lm_pack(xr[i], xr[i + 16]), Ai = lm_pack(xi[i], xi[i + 16]);
+                    const lm_f2 Br = lm_pack(b_lr, b_hr), Bi = lm_pack(b_li, b_hi);
+                    const lm_f2 Er = lm_add2(Ar, Br), Ei = lm_sub2(Ai, Bi), Or = lm_add2(Ai, Bi), Oi = lm_sub2(Br, Ar);
+                    const float2 cs = s_utw[lane + 32 * i];
+                    const lm_f2 C = lm_pack(cs.x, -cs.y), S = lm_pack(cs.y, cs.x), nS = lm_pack(-cs.y, -cs.x);
+                    const lm_f2 Tr = lm_fma2(C, Or, lm_mul2(S, Oi));
+                    const lm_f2 Ti = lm_fma2(C, Oi, lm_mul2(nS, Or));
+                    const lm_f2 Ur = lm_add2(Er, Tr), Ui = lm_add2(Ei, Ti), Vr = lm_sub2(Er, Tr), Vi = lm_sub2(Ei, Ti);
+                    const lm_f2 PU = lm_fma2(Ur, Ur, lm_mul2(Ui, Ui)), PV = lm_fma2(Vr, Vr, lm_mul2(Vi, Vi));
+                    scr[lane + 32 * i] = lm_lo(PU);
+                    scr[lane + 32 * i + 512] = lm_hi(PU);
+                    scr[1024 - lane - 32 * i] = lm_lo(PV);
+                    scr[512 - lane - 32 * i] = lm_hi(PV);
                 }
-                if (lane == 0) scr[512] = 4.0f * fmaf(z16r, z16r, z16i * z16i);
+                {   // lane 0 only: bins 256 and 768 pair with each other (slots 8 and 24), twiddle pi/4
+                    const float ar = xr[8], ai = xi[8], br = xr[24], bi = xi[24];
+                    const float er = ar + br, ei = ai - bi, orr = ai + bi, oi = br - ar;
+                    const float c = 0.70710678118654752440f;
+                    const float tr = c * (orr + oi), ti = c * (oi - orr);
+                    const float ur = er + tr, ui = ei + ti, vr = er - tr, vi = ei - ti;
+                    if (l0) {
+                        scr[256] = fmaf(ur, ur, ui * ui);
+                        scr[768] = fmaf(vr, vr, vi * vi);
+                    }
+                }
             }
         } else {
             // n_fft = 1024: two frames per warp as one complex signal z = a + i b
             const int ta = tf + 2 * warp;
             if (ta < frames) {
+                lm_f2 z[32];
                 float xr[32], xi[32];
                 const float* __restrict__ sa = sb + (2 * warp) * hop;
                 const float* __restrict__ sbb = sa + hop;
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const float w = s_win[32 * n1 + lane];
-                    xr[n1] = sa[32 * n1 + lane] * w;
-                    xi[n1] = sbb[32 * n1 + lane] * w;
+                    z[n1] = lm_mul2(lm_pack(sa[32 * n1 + lane], sbb[32 * n1 + lane]), lm_bcast(w));
                 }
-                warp_cfft1024(xr, xi, scr, s_tw, lane);
+                warp_cfft1024(z, xr, xi, scr, s_tw, lane);
                 // A = Z[k], B = Z[1024-k]:  |Xa|^2 = |A + conj B|^2 / 4, |Xb|^2 = |A - conj B|^2 / 4
                 const int srcl = (32 - lane) & 31;
                 const float z16r = xr[16], z16i = xi[16];
@@ -490,16 +532,23 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                         mma_tf32(acc2, ah2, bh2, ah3, bh3, tf32_lo(w.z, wh2), tf32_lo(w.w, wh3));
                     }
                     // epilogue: c0:(frame g, mel 2tg) c1:(g, 2tg+1) c2:(g+8, 2tg) c3:(g+8, 2tg+1)
+                    const int m0 = mt * 8 + 2 * tg, fl0 = mb * 16 + g;
+                    const int tt0 = tf + fl0, tt1 = tt0 + 8;
+                    const int cf0 = s_ctx[cur].f0, cf1 = s_ctx[cur].f1, ct0 = s_ctx[cur].t0, ct1 = s_ctx[cur].t1;
+                    const bool mk_m0 = (m0 >= cf0) && (m0 < cf1), mk_m1 = (m0 + 1 >= cf0) && (m0 + 1 < cf1);
+                    const bool mk_t0 = (tt0 >= ct0) && (tt0 < ct1), mk_t1 = (tt1 >= ct0) && (tt1 < ct1);
+                    const bool ok_f0 = fl0 < nf, ok_f1 = fl0 + 8 < nf;
+                    const bool ok_m0 = m0 < n_mels, ok_m1 = m0 + 1 < n_mels;
+                    const int o00 = m0 * frames + tt0;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const int f = mb * 16 + g + ((c & 2) ? 8 : 0);
-                        const int m = mt * 8 + 2 * tg + (c & 1);
-                        if (f < nf && m < n_mels) {
-                            const int t = tf + f;
+                        const bool ok = ((c & 2) ? ok_f1 : ok_f0) && ((c & 1) ? ok_m1 : ok_m0);
+                        if (ok) {
+                            const bool masked = ((c & 1) ? mk_m1 : mk_m0) || ((c & 2) ? mk_t1 : mk_t0);
                             const float mp = acc0[c] + (acc1[c] + acc2[c]);
                             float v = (mp <= p.amin) ? p.floor_db : fmaf(p.db_scale, __log2f(mp), -p.db_offset);
-                            if ((m >= ctx.f0 && m < ctx.f1) || (t >= ctx.t0 && t < ctx.t1)) v = 0.0f;
-                            const size_t o = static_cast<size_t>(m) * frames + t;
+                            if (masked) v = 0.0f;
+                            const int o = o00 + ((c & 1) ? frames : 0) + ((c & 2) ? 8 : 0);
                             out[o] = v;
                             if (odb) odb[o] = v;
                             if (omp) omp[o] = mp;
@@ -513,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }
 
         // ---- gather part of the next item (its TMA part is already in flight) -----------------------------
-        if (has_next) stage_gather(nctx, ntile, buf ^ 1);
+        if (has_next) stage_gather(&s_ctx[nslot], ntile, buf ^ 1);
 
         // ---- per-clip normalisation --------------------------------------------------------------------
         if (!next_same_clip) {
@@ -553,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             }
             s_acc = 0.0; q_acc = 0.0;
             clip += gridDim.x;
-            ctx = nctx;
+            cur ^= 1;
             tile = 0;
         } else {
             tile += 1;
