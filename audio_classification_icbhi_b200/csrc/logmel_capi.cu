@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "logmel_kernel.cuh"
+#include "logmel_aux.cuh"
 
 namespace {
 
@@ -316,6 +317,27 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
                           static_cast<cudaStream_t>(cuda_stream));
     if (dev != plan->device) cudaSetDevice(dev);
     return rc;
+}
+
+int lm_resize_finish(const float* in, int32_t B, int32_t n_mels, int32_t frames_in, int32_t frames_out,
+                     const lm_aug* aug, float* out, int32_t normalize, float norm_eps, void* cuda_stream) {
+    if (B < 0 || n_mels < 1 || frames_in < 1 || frames_out < 1) return LM_ERR_INVALID_ARG;
+    if (B == 0) return LM_OK;
+    if (!in || !out || in == out) return LM_ERR_INVALID_ARG;
+    lm::resize_finish_kernel<<<B, lm::kAuxThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        in, out, aug, n_mels, frames_in, frames_out, normalize, norm_eps);
+    LM_CUDA(cudaGetLastError());
+    return LM_OK;
+}
+
+int lm_pcm16_roundtrip(const float* in, float* out, int64_t n, void* cuda_stream) {
+    if (n < 0) return LM_ERR_INVALID_ARG;
+    if (n == 0) return LM_OK;
+    if (!in || !out) return LM_ERR_INVALID_ARG;
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 1023) / 1024, 148 * 8));
+    lm::pcm16_roundtrip_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, out, n);
+    LM_CUDA(cudaGetLastError());
+    return LM_OK;
 }
 
 int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, const int64_t* offset,

@@ -1,0 +1,190 @@
+"""Drop-in `AudioPreprocessor` (reference: R/src/data/preprocessing.py:9-151) on the B200 path.
+
+Same constructor, attributes and method names as the reference class.  `preprocess` returns what
+the reference returns -- a fresh float32 CPU tensor `[1, n_mels, frames]` -- but the arithmetic
+(pad/crop, noise, roll, STFT, mel, dB, masks, normalisation) is one launch of the fused CUDA
+kernel behind `lm_forward`.  New, batched entry points (`preprocess_waveform`,
+`preprocess_batch`) keep features on the GPU for the training loop.
+
+Seeded behaviour: with `augment=True` the random choices are drawn on the host from the same
+global numpy / torch generators, in the same order, as the reference (see augment.py), so
+`set_seed(42)` reproduces the reference's shifts, noise and mask intervals exactly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .augment import draw_fast_augmentation, draw_reference_augmentation
+from .plan import LogMelPlan
+from .wavio import read_wav
+
+__all__ = ["AudioPreprocessor"]
+
+Wave = Union[torch.Tensor, np.ndarray]
+
+
+def _as_mono_1d(w: Wave) -> torch.Tensor:
+    t = torch.as_tensor(w)
+    if t.dim() == 2:   # [C, len] as torchaudio.load returns it
+        t = t.mean(dim=0) if t.shape[0] > 1 else t[0]
+    if t.dim() != 1:
+        raise ValueError(f"waveform must be [len] or [channels, len], got {tuple(t.shape)}")
+    return t.to(torch.float32)
+
+
+class AudioPreprocessor:
+    """Audio preprocessing for respiratory sounds: resampling, log-mel, normalisation, augmentation."""
+
+    freq_mask_param = 15   # T.FrequencyMasking(freq_mask_param=15)   preprocessing.py:52
+    time_mask_param = 35   # T.TimeMasking(time_mask_param=35)        preprocessing.py:53
+    flexible = False
+
+    def __init__(self, sample_rate=16000, n_mels=128, n_fft=2048, hop_length=512, duration=5.0,
+                 augment=False, device=None):
+        self.sample_rate = sample_rate
+        self.n_mels = n_mels
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.duration = duration
+        self.augment = augment
+        self.target_length = int(sample_rate * duration)
+        self._device = device
+        self._plan: Optional[LogMelPlan] = None
+        _lib.load()   # fail loudly at construction if the CUDA library is not built
+
+    # -- plan -------------------------------------------------------------------------------
+    @property
+    def plan(self) -> LogMelPlan:
+        """The GPU plan (window, filterbank, dB constants), created on first use so that the
+        object can be constructed in a DataLoader parent and used after CUDA is initialised."""
+        if self._plan is None:
+            self._plan = LogMelPlan(sample_rate=self.sample_rate, n_fft=self.n_fft, hop_length=self.hop_length,
+                                    n_mels=self.n_mels, target_length=self.target_length, device=self._device)
+        return self._plan
+
+    @property
+    def stft_frames(self) -> int:
+        return 1 + self.target_length // self.hop_length
+
+    @property
+    def frames(self) -> int:
+        """Time steps of the returned feature map."""
+        return self.stft_frames
+
+    # -- reference helper methods (host-side glue, same semantics) ---------------------------------
+    def load_audio(self, audio_path):
+        """File -> `[1, len]` float32 mono at `sample_rate` (preprocessing.py:55-68)."""
+        try:
+            import torchaudio
+            waveform, sr = torchaudio.load(audio_path)
+        except Exception:
+            data, sr = read_wav(str(audio_path))
+            waveform = torch.from_numpy(data)
+        if waveform.shape[0] > 1:
+            waveform = torch.mean(waveform, dim=0, keepdim=True)
+        if sr != self.sample_rate:
+            import torchaudio.transforms as T   # sinc resampler the reference uses (host side)
+            waveform = T.Resample(sr, self.sample_rate)(waveform)
+        return waveform
+
+    def pad_or_crop(self, waveform):
+        """Right zero-pad or centre-crop to `target_length` (preprocessing.py:70-83)."""
+        n = waveform.shape[-1]
+        if n < self.target_length:
+            return torch.nn.functional.pad(waveform, (0, self.target_length - n))
+        if n > self.target_length:
+            start = (n - self.target_length) // 2
+            return waveform[..., start:start + self.target_length]
+        return waveform
+
+    def add_noise(self, waveform, noise_factor=0.005):
+        return waveform + torch.randn_like(waveform) * noise_factor
+
+    def time_shift(self, waveform, shift_max=0.2):
+        shift = int(np.random.uniform(-shift_max, shift_max) * waveform.shape[-1])
+        return torch.roll(waveform, shift, dims=-1)
+
+    def augment_waveform(self, waveform):
+        if np.random.random() > 0.5:
+            waveform = self.add_noise(waveform)
+        if np.random.random() > 0.5:
+            waveform = self.time_shift(waveform)
+        return waveform
+
+    def augment_spectrogram(self, mel_spec):
+        """FrequencyMasking(15) then TimeMasking(35), fill 0.0 (preprocessing.py:105-109)."""
+        from .augment import mask_interval
+        f0, f1 = mask_interval(self.freq_mask_param, mel_spec.shape[-2])
+        t0, t1 = mask_interval(self.time_mask_param, mel_spec.shape[-1])
+        out = mel_spec.clone()
+        out[..., f0:f1, :] = 0.0
+        out[..., :, t0:t1] = 0.0
+        return out
+
+    def normalize(self, mel_spec):
+        return (mel_spec - mel_spec.mean()) / (mel_spec.std() + 1e-8)
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def _draw(self, n: int, fast: bool):
+        if not self.augment:
+            return None, None
+        if fast:
+            return draw_fast_augmentation(n, self.target_length, self.n_mels, self.frames,
+                                          freq_mask_param=self.freq_mask_param,
+                                          time_mask_param=self.time_mask_param), None
+        return draw_reference_augmentation(n, self.target_length, self.n_mels, self.frames,
+                                           freq_mask_param=self.freq_mask_param,
+                                           time_mask_param=self.time_mask_param)
+
+    def _finish(self, plan: LogMelPlan, wave, offset, length, aug, noise, B: int) -> torch.Tensor:
+        """Runs the kernel(s).  Overridden by FlexibleAudioPreprocessor when a resize is needed."""
+        aug_d = plan.upload_aug(aug) if aug is not None else None
+        noise_d = noise.to(plan.device, non_blocking=True) if noise is not None else None
+        return plan.forward(wave, offset, length, aug=aug_d, noise=noise_d)
+
+    def preprocess_batch(self, waveforms: Union[Sequence[Wave], torch.Tensor],
+                         lengths: Optional[Sequence[int]] = None, fast_augment: bool = False) -> torch.Tensor:
+        """Batched hot path.  `waveforms`: list of 1-D / [C, len] waveforms of any lengths (host
+        or device), or a dense `[B, len]` tensor (optionally with per-row `lengths`).
+        Returns `[B, 1, n_mels, frames]` float32 on the GPU."""
+        plan = self.plan
+        dev = plan.device
+        if isinstance(waveforms, torch.Tensor) and waveforms.dim() == 2:
+            B, n = waveforms.shape
+            wave = waveforms.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+            offset = torch.arange(B, device=dev, dtype=torch.int64) * n
+            lens = torch.full((B,), n, dtype=torch.int32) if lengths is None else torch.as_tensor(lengths, dtype=torch.int32)
+            if int(lens.max()) > n:
+                raise ValueError("lengths exceed the row length")
+            length = lens.to(dev)
+        else:
+            clips = [_as_mono_1d(w) for w in waveforms]
+            B = len(clips)
+            lens = [int(c.numel()) for c in clips]
+            starts, pos = [], 0
+            for n in lens:           # 16-byte aligned clip starts: interior tiles go through TMA
+                starts.append(pos)
+                pos += (n + 3) & ~3
+            packed = torch.zeros(max(pos, 4), dtype=torch.float32, device=dev)
+            for s, c in zip(starts, clips):
+                if c.numel():
+                    packed[s:s + c.numel()].copy_(c, non_blocking=True)
+            wave = packed
+            offset = torch.tensor(starts, dtype=torch.int64, device=dev)
+            length = torch.tensor(lens, dtype=torch.int32, device=dev)
+        aug, noise = self._draw(B, fast_augment)
+        return self._finish(plan, wave, offset, length, aug, noise, B)
+
+    def preprocess_waveform(self, waveform: Wave) -> torch.Tensor:
+        """One in-memory waveform -> `[1, n_mels, frames]` float32 CPU tensor (what `preprocess`
+        returns after `load_audio`)."""
+        return self.preprocess_batch([waveform])[0].cpu()
+
+    def preprocess(self, audio_path):
+        """Complete pipeline for one file (preprocessing.py:118-151): load, pad/crop, waveform
+        augmentation, log-mel, dB, SpecAugment, normalise."""
+        return self.preprocess_waveform(self.load_audio(audio_path))

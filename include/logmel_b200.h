@@ -135,6 +135,23 @@ int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, con
                     const int32_t* length, int32_t B, const lm_aug* aug, const float* noise,
                     float* out, int32_t normalize);
 
+/*
+ * FlexibleAudioPreprocessor's tail for durations whose frame count differs from ceil(T/hop)
+ * (R/data/preprocessing_flexible.py:118-154 resize_spectrogram, then :106-110 masks, :112-116
+ * normalize; order of :182-190).  in: dB [B,1,n_mels,frames_in] from lm_forward(normalize=0, no
+ * masks); out: [B,1,n_mels,frames_out].  Device pointers; in != out; aug may be NULL (only
+ * f0,f1,t0,t1 are read, t in output frames).
+ */
+int lm_resize_finish(const float* in, int32_t B, int32_t n_mels, int32_t frames_in, int32_t frames_out,
+                     const lm_aug* aug, float* out, int32_t normalize, float norm_eps, void* cuda_stream);
+
+/*
+ * y = rint(clamp(x,-1,1) * 32767) / 32768: the PCM_16 temp-wav round trip the analyzers put every
+ * window through (R/realtime_analyzer_parallel.py:181-184; soundfile + torchaudio.load, neither in
+ * the reference tree: parity unpinned).  Device pointers; in-place allowed.
+ */
+int lm_pcm16_roundtrip(const float* in, float* out, int64_t n, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

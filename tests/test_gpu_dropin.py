@@ -1,0 +1,198 @@
+"""GPU tests of the drop-in layer: the reference's class contract, served by the CUDA path.
+Run on the B200 box: pytest -m gpu."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import audio_classification_icbhi_b200 as A
+from audio_classification_icbhi_b200 import wavio
+from oracle import logmel_oracle as O
+from tests.golden.make_golden import golden_input
+
+pytestmark = pytest.mark.gpu
+NORM_ATOL = 2e-4
+DB_ATOL = 1e-3
+
+
+def set_seed(seed):   # R/src/utils/config.py:31-33
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def test_preprocess_file_returns_the_reference_contract(tmp_path, golden):
+    """preprocess(path) -> fresh float32 CPU tensor [1, n_mels, frames] (R/diagnose_data.py:55-66)."""
+    x = golden_input(0, 80000)
+    path = str(tmp_path / "clip.wav")
+    wavio.write_wav_pcm16(path, x, 16000)
+    p = A.AudioPreprocessor()
+    out = p.preprocess(path)
+    assert isinstance(out, torch.Tensor) and out.device.type == "cpu" and out.dtype == torch.float32
+    assert tuple(out.shape) == (1, 128, 157) and torch.isfinite(out).all()
+    xq = np.rint(x.astype(np.float64) * 32767) / 32768.0           # what the PCM_16 file holds
+    assert np.abs(out[0].numpy() - O.logmel(xq.astype(np.float32), O.OracleConfig())).max() < NORM_ATOL
+    # and an in-memory clip reproduces the reference's own output
+    out2 = p.preprocess_waveform(torch.from_numpy(x).unsqueeze(0))
+    assert np.abs(out2[0].numpy() - golden["headline_5s/norm"]).max() < NORM_ATOL
+    # stereo input is averaged to mono like load_audio does
+    out3 = p.preprocess_waveform(torch.from_numpy(np.stack([x, x])))
+    assert torch.equal(out3, out2)
+
+
+@pytest.mark.parametrize("tag,dur", [("aug_3s", 3.0), ("aug_5s", 5.0)])
+def test_seeded_training_path_reproduces_the_reference(golden, tag, dur):
+    """Config 4: set_seed(42), augment=True, clips one by one (the reference's call pattern) and as
+    one batch: both give the reference's seeded outputs."""
+    T = int(16000 * dur)
+    clips = [golden_input(100 + c, T) for c in range(6)]
+    set_seed(42)
+    p = A.AudioPreprocessor(duration=dur, augment=True)
+    one_by_one = [p.preprocess_waveform(torch.from_numpy(c).unsqueeze(0)) for c in clips]
+    set_seed(42)
+    batched = p.preprocess_batch(clips).cpu()
+    for c in range(6):
+        ref = golden[f"{tag}/clip{c}/norm"]
+        assert np.abs(one_by_one[c][0].numpy() - ref).max() < NORM_ATOL
+        assert torch.equal(batched[c], one_by_one[c])
+    # throughput mode: on-device noise, private RNG -- valid features, masks inside the bounds
+    fast = p.preprocess_batch(clips, fast_augment=True)
+    assert torch.isfinite(fast).all() and fast.shape == batched.shape
+
+
+def test_flexible_resize_8s_matches_reference(golden):
+    x = golden_input(7, 128000)
+    f = A.FlexibleAudioPreprocessor(duration=8.0)
+    out = f.preprocess_waveform(x)
+    assert tuple(out.shape) == (1, 128, 250)
+    assert np.abs(out[0].numpy() - golden["flex_8s_resize/norm"]).max() < NORM_ATOL
+    # resize_spectrogram on its own, host tensor in -> host tensor out, equals F.interpolate
+    db = torch.from_numpy(golden["cfg_8s/db"]).unsqueeze(0)
+    r = f.resize_spectrogram(db)
+    assert r.device.type == "cpu" and tuple(r.shape) == (1, 128, 250)
+    ref = torch.nn.functional.interpolate(db.unsqueeze(0), size=(128, 250), mode="bilinear", align_corners=False)[0]
+    assert (r - ref).abs().max().item() < 1e-4
+    assert np.abs(r[0].numpy() - golden["flex_8s_resize/db"]).max() < DB_ATOL
+    assert f.resize_spectrogram(torch.zeros(1, 128, 250)).shape[-1] == 250      # no-op when sizes agree
+
+
+def test_flexible_resize_with_masks_acts_on_resized_axis():
+    set_seed(3)
+    f = A.FlexibleAudioPreprocessor(duration=8.0, augment=True)
+    x = golden_input(12, 128000)
+    set_seed(3)
+    aug, noise = A.draw_reference_augmentation(1, 128000, 128, 250)
+    set_seed(3)
+    out = f.preprocess_batch([x]).cpu().numpy()[0, 0]
+    a = aug[0]
+    ref = O.logmel(x, O.OracleConfig(duration=8.0), flexible=True, shift=int(a["shift"]),
+                   noise=None if noise is None else noise[0].numpy(), noise_scale=float(a["noise_scale"]),
+                   masks=(int(a["f0"]), int(a["f1"]), int(a["t0"]), int(a["t1"])))
+    assert out.shape == (128, 250)
+    assert np.abs(out - ref).max() < NORM_ATOL
+
+
+@pytest.mark.parametrize("seg,overlap,n_fft", [(1.0, 0.5, 2048), (0.5, 0.75, 1024)])
+def test_sliding_windows_match_per_window_oracle(seg, overlap, n_fft):
+    """Config 5 in miniature: every window is an independent clip (own reflect padding, own
+    normalisation), the tail window is zero padded."""
+    sw = A.SlidingWindowLogMel(segment_duration=seg, overlap=overlap)
+    assert sw.preprocessor.n_fft == n_fft
+    rs = np.random.RandomState(9)
+    n = 15 * 16000 + 1234
+    rec = (rs.standard_normal(n) * 0.1).astype(np.float32)
+    feats, times = sw(rec)
+    starts, lengths, times2 = A.segment_offsets(n, 16000, seg, overlap)
+    assert feats.shape == (len(starts), 1, 128, 32) and times == times2
+    n_fft_o, hop_o = O.flexible_fft_params(16000, min(2048, int(16000 * seg / 2)), 256 if seg < 1 else 512, seg)
+    cfg = O.OracleConfig(n_fft=n_fft_o, hop_length=hop_o, duration=seg)
+    got = feats.cpu().numpy()
+    for w in (0, 1, len(starts) // 2, len(starts) - 2, len(starts) - 1):
+        s, l = int(starts[w]), int(lengths[w])
+        assert np.abs(got[w, 0] - O.logmel(rec[s:s + l], cfg)).max() < NORM_ATOL, w
+    # a shard of the windows equals the same rows of the full run (multi-GPU layout)
+    part, _ = sw(rec, window_range=(5, 17))
+    assert torch.equal(part, feats[5:17])
+    # optional PCM_16 round-trip emulation
+    swq = A.SlidingWindowLogMel(segment_duration=seg, overlap=overlap, emulate_pcm16=True)
+    fq, _ = swq(rec)
+    recq = (np.rint(np.clip(rec, -1, 1).astype(np.float64) * 32767) / 32768.0).astype(np.float32)
+    s, l = int(starts[3]), int(lengths[3])
+    assert np.abs(fq[3, 0].cpu().numpy() - O.logmel(recq[s:s + l], cfg)).max() < NORM_ATOL
+
+
+def test_hour_long_recording_window_count_and_spot_checks():
+    """Config 5 at full size: 1 h at 16 kHz, 1 s windows, 50 % overlap -> 7200 windows."""
+    sw = A.SlidingWindowLogMel(segment_duration=1.0, overlap=0.5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    rec = torch.randn(3600 * 16000, generator=g, device="cuda") * 0.1
+    feats, times = sw(rec)
+    torch.cuda.synchronize()
+    assert feats.shape == (7200, 1, 128, 32) and times[-1] == (3599.5, 3600.0)
+    assert torch.isfinite(feats).all()
+    flat = feats.view(7200, -1).double()
+    assert flat.mean(dim=1).abs().max().item() < 1e-5 and (flat.std(dim=1) - 1).abs().max().item() < 1e-5
+    cfg = O.OracleConfig(duration=1.0)
+    for w in (0, 3333, 7198, 7199):
+        s = w * 8000
+        ref = O.logmel(rec[s:s + 16000].cpu().numpy(), cfg)
+        assert np.abs(feats[w, 0].cpu().numpy() - ref).max() < NORM_ATOL
+
+
+def test_datasets_end_to_end_with_gpu_collate(tmp_path):
+    d = tmp_path / "audio_and_txt_files"
+    d.mkdir()
+    rs = np.random.RandomState(1)
+    sigs = []
+    for i in range(10):
+        x = (rs.standard_normal(16000 * (2 + i % 3)) * 0.1).clip(-1, 1)
+        sigs.append(x)
+        wavio.write_wav_pcm16(str(d / f"{100 + i}_r.wav"), x, 16000)
+        (d / f"{100 + i}_r.txt").write_text(f"0.0\t1.0\t{i % 2}\t0\n")
+    cfg = {"data": dict(sample_rate=16000, n_mels=128, n_fft=2048, hop_length=512, duration=3.0)}
+    ds = A.ICBHIDataset(tmp_path, "train", cfg, augment=False)
+    mel, label = ds[2]                                   # the reference's __getitem__ contract
+    assert mel.device.type == "cpu" and tuple(mel.shape) == (1, 128, 94) and label == 0
+    loader = torch.utils.data.DataLoader(ds.raw(), batch_size=4, shuffle=False, num_workers=0,
+                                         collate_fn=A.GpuCollate(ds.preprocessor))
+    feats, labels = next(iter(loader))
+    assert feats.is_cuda and feats.shape == (4, 1, 128, 94) and labels.tolist() == [0, 1, 0, 1]
+    assert torch.allclose(feats[2].cpu(), mel, atol=1e-6)
+    xq = (np.rint(sigs[2] * 32767) / 32768.0).astype(np.float32)
+    assert np.abs(mel[0].numpy() - O.logmel(xq, O.OracleConfig(duration=3.0))).max() < NORM_ATOL
+
+
+def test_segmenter_gpu_shortcut(tmp_path):
+    rs = np.random.RandomState(4)
+    x = (rs.standard_normal(16000 * 9) * 0.1).clip(-1, 1)
+    wavio.write_wav_pcm16(str(tmp_path / "a.wav"), x, 16000)
+    (tmp_path / "a.txt").write_text("0.1\t2.6\t0\t0\n2.6\t2.9\t1\t0\n2.9\t8.95\t1\t1\n")
+    seg = A.ICBHISegmenter(tmp_path, tmp_path / "out")
+    p = A.AudioPreprocessor()
+    feats, labels = seg.segments_to_features(tmp_path / "a.wav", tmp_path / "a.txt", p)
+    assert labels == ["normal", "both"] and feats.shape == (2, 1, 128, 157)
+    xq = (np.rint(x * 32767) / 32768.0).astype(np.float32)
+    for i, (a, b) in enumerate(((0.1, 2.6), (2.9, 8.95))):
+        ref = O.logmel(xq[int(a * 16000):int(b * 16000)], O.OracleConfig())
+        assert np.abs(feats[i, 0].cpu().numpy() - ref).max() < NORM_ATOL
+
+
+@pytest.mark.parametrize("n_mels,hop,dur", [(64, 512, 2.0), (40, 256, 1.5), (128, 128, 1.0), (200, 512, 2.0)])
+def test_other_configurations_match_oracle(n_mels, hop, dur):
+    """The config keys are inputs, not constants: other n_mels / hop values go through the same kernel."""
+    p = A.AudioPreprocessor(n_mels=n_mels, hop_length=hop, duration=dur)
+    x = golden_input(31, int(16000 * dur) + 777)
+    out = p.preprocess_waveform(x)[0].numpy()
+    cfg = O.OracleConfig(n_mels=n_mels, hop_length=hop, duration=dur)
+    assert out.shape == (n_mels, cfg.frames)
+    fb = A.reference_filterbank(1025, n_mels, 16000).numpy()
+    assert np.abs(out - O.logmel(x, cfg, fb=fb)).max() < NORM_ATOL
+
+
+def test_unsupported_configurations_fail_loudly():
+    for kw in (dict(n_fft=4096), dict(n_fft=2000), dict(hop_length=511), dict(hop_length=1024), dict(n_mels=300)):
+        with pytest.raises(RuntimeError, match="unsupported configuration"):
+            A.AudioPreprocessor(**kw).plan
+    with pytest.raises(RuntimeError, match="target_len must exceed"):
+        A.AudioPreprocessor(duration=0.05).plan
