@@ -97,10 +97,14 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     k.B = B; k.normalize = normalize;
     const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
     const int grid = std::min<int>(B, cap);
-    if (p->n_fft == 2048)
-        lm::logmel_kernel<2048><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
-    else
-        lm::logmel_kernel<1024><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
+    if (p->n_fft == 2048) {
+        if (extra) lm::logmel_kernel<2048, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+        else lm::logmel_kernel<2048, false><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    } else {
+        if (extra) lm::logmel_kernel<1024, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+        else lm::logmel_kernel<1024, false><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    }
     LM_CUDA(cudaGetLastError());
     ++p->launches;
     return LM_OK;
@@ -264,13 +268,19 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     // ---- shared memory --------------------------------------------------------------------
     cudaError_t e;
     if (p->n_fft == 2048) {
-        p->smem_bytes = lm::Smem<2048>(p->ns, p->n_dk).total;
-        e = cudaFuncSetAttribute(lm::logmel_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        p->smem_bytes = lm::Smem<2048>::total(p->ns, p->n_dk);
+        e = cudaFuncSetAttribute(lm::logmel_kernel<2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(p->smem_bytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm::logmel_kernel<2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(p->smem_bytes));
     } else {
-        p->smem_bytes = lm::Smem<1024>(p->ns, p->n_dk).total;
-        e = cudaFuncSetAttribute(lm::logmel_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        p->smem_bytes = lm::Smem<1024>::total(p->ns, p->n_dk);
+        e = cudaFuncSetAttribute(lm::logmel_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(p->smem_bytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm::logmel_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(p->smem_bytes));
     }
     if (e != cudaSuccess) { free_plan(p); return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
     *out_plan = p;

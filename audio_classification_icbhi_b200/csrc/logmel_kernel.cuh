@@ -2,9 +2,12 @@
 //
 // One persistent CTA per SM (16 warps).  A CTA takes whole clips (blockIdx.x, += gridDim.x) and
 // walks a flat list of work items (clip, tile); a tile is 16 frames (32 for n_fft = 1024).
-// Per item:
+// Two CTA barriers per item: X sits in the MIDDLE of the FFT (before the transpose first touches
+// the power rows), Y after it.  A warp that finishes its share of the mel phase of item i therefore
+// runs straight into the register-only first half of the FFT of item i+1 while slower warps are
+// still on the tensor cores.  Per item:
 //
-//   stage   (done one item AHEAD, into the other buffer) the tile's samples -> shared memory,
+//   stage   (done TWO items ahead, into the buffer just consumed) the tile's samples -> shared memory,
 //           once per sample although every sample feeds 4 frames.  The contiguous interior of
 //           a plain clip is one cp.async.bulk (TMA, 1-D) completing on an mbarrier; whatever
 //           is left -- torch.stft's reflect padding, zero padding, and whole tiles of augmented
@@ -32,6 +35,23 @@
 
 #include "../../include/logmel_b200.h"
 #include "fft_gen.cuh"
+
+// Build-time experiment switches (tools/build_variants.py); the defaults are the shipped kernel.
+#ifndef LM_TW2
+#define LM_TW2 1      // 1: twiddle = product of two table entries (10 loads); 0: 31 table loads
+#endif
+#ifndef LM_ALWAYS_ACTIVE
+#define LM_ALWAYS_ACTIVE 1   // 1: warps whose frame is past the clip end compute anyway (no divergent join)
+#endif
+#ifndef LM_STAGGER_NS
+#define LM_STAGGER_NS 0     // > 0: warps of one scheduler start the FFT (warp/4) * ns apart
+#endif
+#ifndef LM_F32_TILE_STATS
+#define LM_F32_TILE_STATS 0 // 1: per-thread per-tile sums in fp32, accumulated across tiles in fp64
+#endif
+#ifndef LM_SPLIT
+#define LM_SPLIT 1    // 1: CTA barrier X between the two halves of the FFT; 0: before the FFT
+#endif
 
 namespace lm {
 
@@ -122,6 +142,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// Opaque copy: stops the compiler from hoisting address arithmetic that depends on `v` out of the
+// item loop and keeping it alive across the register-heavy FFT (it is recomputed per phase instead).
+__device__ __forceinline__ int launder(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
@@ -148,20 +174,48 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 1024-point complex FFT of one warp.  On entry lane n2 holds z[32*n1 + n2] in z[n1] (re, im packed
-// in one 64-bit register); on exit lane k1 holds Z[k1 + 32*k2] in (xr[k2], xi[k2]).
-// `scr` is the warp's private row.  First FFT: packed complex (FFMA2/FADD2); the transpose moves the
-// real and imaginary planes separately and its LDS.128 reads hand the second FFT register pairs of
-// neighbouring points, which is the layout its packed stages 1-4 want (see gen_fft.py).
+// 1024-point complex FFT of one warp, in two halves so that a CTA barrier can sit between them.
+// On entry lane n2 holds z[32*n1 + n2] in z[n1] (re, im packed in one 64-bit register); on exit lane
+// k1 holds Z[k1 + 32*k2] in (xr[k2], xi[k2]).
+//   part 1 (registers only): packed complex radix-32 FFT over the lane-local index;
+//   part 2: twiddle, 32x32 transpose through the warp's private row `scr` (real and imaginary planes
+//           separately; the LDS.128 reads hand the second FFT register pairs of neighbouring
+//           points, the layout its packed stages 1-4 want -- see gen_fft.py) + second radix-32 FFT.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_cfft1024(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
-                                              float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
-    lm_fft32_aos(z);
+__device__ __forceinline__ void warp_cfft1024_part1(lm_f2 (&z)[32]) { lm_fft32_aos(z); }
+__device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
+                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
+#if LM_TW2
+    // Twiddle W1024^(lane*k1), k1 = 4a + b, as the product of two table entries W^(4a*lane) * W^(b*lane):
+    // 10 shared-memory loads instead of 31 (the shared-memory pipe is the tighter resource here, and
+    // 31 loads in flight on top of z do not fit the register file), one extra rounding per twiddle.
+    // tw holds (cos, -sin); (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy).
+    auto cmul = [](lm_f2 v, lm_f2 w) {
+        return lm_fma2(lm_swap(v), lm_pack(-lm_hi(w), lm_hi(w)), lm_mul2(v, lm_bcast(lm_lo(w))));
+    };
+    auto ldtw = [&](int k1) {
+        const float2 w = tw[k1 * 32 + lane];
+        return lm_pack(w.x, w.y);
+    };
+    const lm_f2 B1 = ldtw(1), B2 = ldtw(2), B3 = ldtw(3);
+    z[1] = cmul(z[1], B1);
+    z[2] = cmul(z[2], B2);
+    z[3] = cmul(z[3], B3);
+#pragma unroll
+    for (int a = 1; a < 8; ++a) {
+        const lm_f2 A = ldtw(4 * a);
+        z[4 * a] = cmul(z[4 * a], A);
+        z[4 * a + 1] = cmul(z[4 * a + 1], cmul(A, B1));
+        z[4 * a + 2] = cmul(z[4 * a + 2], cmul(A, B2));
+        z[4 * a + 3] = cmul(z[4 * a + 3], cmul(A, B3));
+    }
+#else
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
         const float2 w = tw[k1 * 32 + lane];   // (cos, -sin): (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy)
         z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-w.y, w.y), lm_mul2(z[k1], lm_bcast(w.x)));
     }
+#endif
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -193,30 +247,31 @@ struct Geo {
     static constexpr int MT = TILE_F / 16;               // 16-frame MMA row blocks per tile
 };
 
-// Shared-memory carve-up, shared by host (size) and device (pointers).
+// Shared-memory carve-up, shared by host (size) and device (pointers).  Everything of fixed size
+// comes first so that its addresses are compile-time constants (no registers spent on pointers);
+// the two run-time sized arrays (staging buffers, filterbank) sit at the end.
 template <int NFFT>
 struct Smem {
-    static __host__ __device__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-    size_t o_bar, o_red, o_ctx, o_tab, o_sbuf, o_scr, o_win, o_tw, o_utw, o_melw, total;
-    __host__ __device__ Smem(int ns, int n_dk) {
-        size_t o = 0;
-        o_bar = o; o += 16;
-        o_red = o; o += sizeof(double) * 2 * kWarps + 16;
-        o = align16(o);
-        o_ctx = o; o += 2 * 64;                       // two ClipCtx slots
-        o_tab = o; o += align16(sizeof(MelTable));
-        o_sbuf = o; o += sizeof(float) * 2 * static_cast<size_t>(ns);
-        o_scr = o; o += sizeof(float) * kWarps * kRowFloats;
-        o_win = o; o += sizeof(float) * NFFT;
-        o_tw = o; o += sizeof(float2) * 1024;
-        o_utw = o; o += (NFFT == 2048) ? sizeof(float2) * 512 : 0;
-        o_melw = o; o += sizeof(float4) * 32 * static_cast<size_t>(n_dk);
-        total = o;
+    static constexpr size_t kBar = 0;                                    // 2 mbarriers + 2 'TMA pending' flags
+    static constexpr size_t kRed = kBar + 32;                            // block-reduction scratch + broadcast
+    static constexpr size_t kCtx = kRed + sizeof(double) * 2 * kWarps + 16;   // four ClipCtx slots (ordinal & 3)
+    static constexpr size_t kTab = kCtx + 4 * 64;
+    static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fp64 (sum, sumsq)
+    static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
+    static constexpr size_t kTw = kWin + sizeof(float) * NFFT;
+    static constexpr size_t kUtw = kTw + sizeof(float2) * 1024;
+    static constexpr size_t kScr = kUtw + ((NFFT == 2048) ? sizeof(float2) * 512 : 0);
+    static constexpr size_t kSbuf = kScr + sizeof(float) * kWarps * kRowFloats;
+    static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0, "alignment");
+    static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * 2 * static_cast<size_t>(ns); }
+    static __host__ __device__ size_t total(int ns, int n_dk) {
+        return melw_offset(ns) + sizeof(float4) * 32 * static_cast<size_t>(n_dk);
     }
 };
 
-// Everything the staging and epilogue code needs to know about one clip.  Two slots live in
-// shared memory (current / next clip) so that none of it occupies registers across the FFT phase.
+// Everything the staging and epilogue code needs to know about one clip.  Four slots live in
+// shared memory (clip ordinal & 3: staging runs two items ahead of the epilogue) so that none of
+// it occupies registers across the FFT.
 struct ClipCtx {
     const float* src;    // first sample after the centre crop
     const float* nz;     // host-drawn noise row or nullptr
@@ -249,28 +304,29 @@ __device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* _
     c->plain = (shift == 0) && (nscale == 0.0f) && (gain == 1.0f);
 }
 
-template <int NFFT>
+template <int NFFT, bool EXTRA_OUT>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     using G = Geo<NFFT>;
     constexpr int TILE_F = G::TILE_F;
     constexpr int HALF = NFFT / 2;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const Smem<NFFT> L(p.ns, p.n_dk);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.o_bar);
-    double* red = reinterpret_cast<double*>(smem_raw + L.o_red);
-    float* bcast = reinterpret_cast<float*>(smem_raw + L.o_red + sizeof(double) * 2 * kWarps);
-    ClipCtx* s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L.o_ctx);
-    const MelTable* s_tab = reinterpret_cast<const MelTable*>(smem_raw + L.o_tab);
-    float* sbuf = reinterpret_cast<float*>(smem_raw + L.o_sbuf);
-    float* scr_all = reinterpret_cast<float*>(smem_raw + L.o_scr);
-    float* s_win = reinterpret_cast<float*>(smem_raw + L.o_win);
-    float2* s_tw = reinterpret_cast<float2*>(smem_raw + L.o_tw);
-    float2* s_utw = reinterpret_cast<float2*>(smem_raw + L.o_utw);
-    float4* s_melw = reinterpret_cast<float4*>(smem_raw + L.o_melw);
+    using L = Smem<NFFT>;
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + L::kBar);
+    volatile int* const s_pend = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 16);
+    double* const red = reinterpret_cast<double*>(smem_raw + L::kRed);
+    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + sizeof(double) * 2 * kWarps);
+    ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx);
+    const MelTable* const s_tab = reinterpret_cast<const MelTable*>(smem_raw + L::kTab);
+    double2* const s_stat = reinterpret_cast<double2*>(smem_raw + L::kStat);
+    float* const s_win = reinterpret_cast<float*>(smem_raw + L::kWin);
+    float2* const s_tw = reinterpret_cast<float2*>(smem_raw + L::kTw);
+    float2* const s_utw = reinterpret_cast<float2*>(smem_raw + L::kUtw);
+    float* const scr_all = reinterpret_cast<float*>(smem_raw + L::kScr);
+    float* const sbuf = reinterpret_cast<float*>(smem_raw + L::kSbuf);
+    float4* const s_melw = reinterpret_cast<float4*>(smem_raw + L::melw_offset(p.ns));
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* scr = scr_all + warp * kRowFloats;
+    const int tid = threadIdx.x, lane_ = tid & 31, warp_ = tid >> 5;
 
     const int n_my = (p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     if (n_my <= 0) return;
@@ -283,12 +339,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
     for (int i = tid; i < 32 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
     for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
-        reinterpret_cast<int*>(smem_raw + L.o_tab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
+        reinterpret_cast<int*>(smem_raw + L::kTab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
     for (int i = tid; i < kWarps * kRowFloats; i += kThreads) scr_all[i] = 0.0f;   // pad columns stay finite
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         fence_mbar_init();
+        s_pend[0] = 0;
+        s_pend[1] = 0;
     }
     __syncthreads();
 
@@ -312,18 +370,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         e_lo = lo;
         cnt = (hi - lo) & ~3;
     };
-    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_, int buf) -> bool {   // thread 0 issues; all agree
+    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_, int buf) {   // ONE thread
         int e_lo, cnt;
         bulk_range(c, tile_, e_lo, cnt);
-        if (cnt == 0) return false;
-        if (tid == 0) {
+        if (cnt != 0) {
             const int j0 = tile_ * TILE_F * hop - HALF;
             fence_proxy_async();
             mbar_expect_tx(&mbar[buf], static_cast<uint32_t>(cnt) * 4u);
             bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u,
                      &mbar[buf]);
         }
-        return true;
+        s_pend[buf] = (cnt != 0);
     };
     auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_, int buf) {   // all threads
         const ClipCtx c = *cc;
@@ -357,51 +414,44 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }
     };
 
-    uint32_t parity0 = 0, parity1 = 0;     // mbarrier phase per staging buffer (CTA-uniform)
-    bool pending0 = false, pending1 = false;
-
-    int clip = blockIdx.x;
-    int cur = 0;                       // s_ctx[cur] = this clip, s_ctx[cur ^ 1] = the next one
-    if (tid == 0) load_clip(p, clip, &s_ctx[0]);
+    // ---- prologue: items 0 and 1 are staged before the loop; item it+2 is staged during item it ------
+    const int clip0 = blockIdx.x, cstride = gridDim.x;
+    if (tid == 0) {
+        load_clip(p, clip0, &s_ctx[0]);
+        if (p.n_tiles == 1 && n_items > 1) load_clip(p, clip0 + cstride, &s_ctx[1]);
+        stage_bulk(&s_ctx[0], 0, 0);
+        if (n_items > 1) stage_bulk(&s_ctx[p.n_tiles == 1 ? 1 : 0], p.n_tiles == 1 ? 0 : 1, 1);
+    }
     __syncthreads();
-    pending0 = stage_bulk(&s_ctx[0], 0, 0);
     stage_gather(&s_ctx[0], 0, 0);
-    double s_acc = 0.0, q_acc = 0.0;
-    int tile = 0;
+    if (n_items > 1) stage_gather(&s_ctx[p.n_tiles == 1 ? 1 : 0], p.n_tiles == 1 ? 0 : 1, 1);
+    __syncthreads();
+
+    uint32_t parity0 = 0, parity1 = 0;     // mbarrier phase per staging buffer (CTA-uniform)
+    s_stat[tid] = make_double2(0.0, 0.0);  // this thread's running (sum, sum of squares) of the clip's dB values
+    int tile = 0, ord = 0;                 // tile index and clip ordinal of item `it`
 
 #pragma unroll 1
     for (int it = 0; it < n_items; ++it) {
         const int buf = it & 1;
         const int tf = tile * TILE_F;                  // first frame of the tile
+        const int clip = clip0 + ord * cstride;
         const float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
-        if (buf ? pending1 : pending0) {
+        if (s_pend[buf]) {
             mbar_wait(&mbar[buf], buf ? parity1 : parity0);
-            if (buf) { parity1 ^= 1u; pending1 = false; } else { parity0 ^= 1u; pending0 = false; }
-        }
-        __syncthreads();   // (A) item staged (gather part written last iteration); rows free again
-
-        // ---- next item: TMA now, gather after the mel phase ---------------------------------------
-        const bool has_next = (it + 1 < n_items);
-        const bool next_same_clip = (tile + 1 < p.n_tiles);
-        const int ntile = next_same_clip ? tile + 1 : 0;
-        const int nslot = next_same_clip ? cur : (cur ^ 1);
-        if (has_next && !next_same_clip) {
-            // the next clip's slot is idle (its previous owner finished a whole clip ago); every
-            // thread needs it right now for the uniform TMA decision, so one warp-wide sync it is
-            if (tid == 0) load_clip(p, clip + gridDim.x, &s_ctx[nslot]);
-            __syncthreads();
-        }
-        if (has_next) {
-            const bool issued = stage_bulk(&s_ctx[nslot], ntile, buf ^ 1);
-            if (buf) pending0 = issued; else pending1 = issued;
+            if (buf) parity1 ^= 1u; else parity0 ^= 1u;
         }
 
-        // ---- FFT phase: one frame per warp -> 4|X|^2 in the warp's row -------------------------------
-        if (NFFT == 2048) {
-            const int t = tf + warp;
-            if (t < frames) {
-                lm_f2 z[32];
-                float xr[32], xi[32];
+#if !LM_SPLIT
+        __syncthreads();   // (X) placed before the FFT: experiment baseline
+#endif
+        // ---- FFT part 1 (registers + reads of the staged samples only) ----------------------------------
+        lm_f2 z[32];
+        const bool active = LM_ALWAYS_ACTIVE ? true : ((NFFT == 2048) ? (tf + warp_ < frames) : (tf + 2 * warp_ < frames));
+        if (LM_STAGGER_NS > 0) __nanosleep((warp_ >> 2) * LM_STAGGER_NS);
+        if (active) {
+            const int lane = launder(lane_), warp = launder(warp_);
+            if (NFFT == 2048) {
                 const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
 #pragma unroll
@@ -410,15 +460,38 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     const float2 w = w2[32 * n1 + lane];
                     z[n1] = lm_mul2(lm_pack(v.x, v.y), lm_pack(w.x, w.y));
                 }
-                warp_cfft1024(z, xr, xi, scr, s_tw, lane);
+            } else {
+                // n_fft = 1024: two frames per warp as one complex signal z = a + i b
+                const float* __restrict__ sa = sb + (2 * warp) * hop;
+                const float* __restrict__ sbb = sa + hop;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float w = s_win[32 * n1 + lane];
+                    z[n1] = lm_mul2(lm_pack(sa[32 * n1 + lane], sbb[32 * n1 + lane]), lm_bcast(w));
+                }
+            }
+            warp_cfft1024_part1(z);
+        }
+#if LM_SPLIT
+        __syncthreads();   // (X) every warp is done with the mel phase of the previous item (rows are
+                           //     free) and with this item's staged samples (buffer `buf` is free)
+#endif
+
+        // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
+        if (active) {
+            const int lane = launder(lane_), warp = launder(warp_);
+            float* const scr = scr_all + warp * kRowFloats;
+            float xr[32], xi[32];
+            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane);
+            const int srcl = (32 - lane) & 31;
+            const bool l0 = (lane == 0);
+            if (NFFT == 2048) {
                 // Real-FFT untangle.  Bin k = lane + 32*k2 pairs with 1024-k, which lives in lane
                 // (32-lane)&31 at slot 31-k2 (lane 0: slot (32-k2)&31) and comes over by warp shuffle.
                 // Two pairs per packed op: k2 = i (lo half) and k2 = i+16 (hi half), i = 0..7; their
                 // partners are the other lane's slots 31-i and 15-i, and the hi twiddle is the lo one
-                // turned by pi/2: (c, s)(k+512) = (-s, c)(k).  The row was last read inside
-                // warp_cfft1024 (followed by __syncwarp): 4|X|^2 goes straight into it, bin-major.
-                const int srcl = (32 - lane) & 31;
-                const bool l0 = (lane == 0);
+                // turned by pi/2: (c, s)(k+512) = (-s, c)(k).  The row was last read inside part 2
+                // (followed by __syncwarp): 4|X|^2 goes straight into it, bin-major.
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float s_lr = l0 ? xr[(32 - i) & 31] : xr[31 - i];
@@ -454,23 +527,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                         scr[768] = fmaf(vr, vr, vi * vi);
                     }
                 }
-            }
-        } else {
-            // n_fft = 1024: two frames per warp as one complex signal z = a + i b
-            const int ta = tf + 2 * warp;
-            if (ta < frames) {
-                lm_f2 z[32];
-                float xr[32], xi[32];
-                const float* __restrict__ sa = sb + (2 * warp) * hop;
-                const float* __restrict__ sbb = sa + hop;
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float w = s_win[32 * n1 + lane];
-                    z[n1] = lm_mul2(lm_pack(sa[32 * n1 + lane], sbb[32 * n1 + lane]), lm_bcast(w));
-                }
-                warp_cfft1024(z, xr, xi, scr, s_tw, lane);
+            } else {
                 // A = Z[k], B = Z[1024-k]:  |Xa|^2 = |A + conj B|^2 / 4, |Xb|^2 = |A - conj B|^2 / 4
-                const int srcl = (32 - lane) & 31;
                 const float z16r = xr[16], z16i = xi[16];
                 float* Pa = scr;
                 float* Pb = scr + kPbOff;
@@ -478,27 +536,40 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 for (int k2 = 0; k2 < 16; ++k2) {
                     float br = __shfl_sync(0xffffffffu, xr[31 - k2], srcl);
                     float bi = __shfl_sync(0xffffffffu, xi[31 - k2], srcl);
-                    if (lane == 0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
+                    if (l0) { br = xr[(32 - k2) & 31]; bi = xi[(32 - k2) & 31]; }
                     const float ar = xr[k2], ai = xi[k2];
                     const float ur = ar + br, ui = ai - bi, vr = ar - br, vi = ai + bi;
                     Pa[lane + 32 * k2] = fmaf(ur, ur, ui * ui);
                     Pb[lane + 32 * k2] = fmaf(vr, vr, vi * vi);
                 }
-                if (lane == 0) {   // k = 512 pairs with itself: A = B
+                if (l0) {   // k = 512 pairs with itself: A = B
                     Pa[512] = 4.0f * z16r * z16r;
                     Pb[512] = 4.0f * z16i * z16i;
                 }
             }
         }
-        __syncthreads();   // (B) all power rows of the tile are in shared memory
+        // ---- item it+2: its TMA part goes into the buffer consumed before (X).  Issued here, where no
+        //      FFT registers are live, by one thread; the clip's context slot is filled when its first
+        //      tile comes up. ------------------------------------------------------------------------------
+        const bool has2 = (it + 2 < n_items);
+        int tile2 = tile + 2, ord2 = ord;
+        while (tile2 >= p.n_tiles) { tile2 -= p.n_tiles; ++ord2; }
+        if (has2 && tid == 0) {
+            if (tile2 == 0) load_clip(p, clip0 + ord2 * cstride, &s_ctx[ord2 & 3]);
+            stage_bulk(&s_ctx[ord2 & 3], tile2, buf);
+        }
+        __syncthreads();   // (Y) all power rows of the tile are in shared memory
 
         // ---- mel phase: tensor cores, one 8-mel column block per warp ---------------------------------
         {
+            const int lane = launder(lane_), warp = launder(warp_);
             const int g = lane >> 2, tg = lane & 3;
             const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+            const ClipCtx* __restrict__ cx = &s_ctx[ord & 3];
+            double s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
             float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
-            float* __restrict__ odb = p.out_db ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
-            float* __restrict__ omp = p.out_melpow ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
 #pragma unroll 1
             for (int slot = 0; slot < 2; ++slot) {
                 const int mt = s_tab->warp_tile[warp][slot];
@@ -534,12 +605,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     // epilogue: c0:(frame g, mel 2tg) c1:(g, 2tg+1) c2:(g+8, 2tg) c3:(g+8, 2tg+1)
                     const int m0 = mt * 8 + 2 * tg, fl0 = mb * 16 + g;
                     const int tt0 = tf + fl0, tt1 = tt0 + 8;
-                    const int cf0 = s_ctx[cur].f0, cf1 = s_ctx[cur].f1, ct0 = s_ctx[cur].t0, ct1 = s_ctx[cur].t1;
+                    const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
                     const bool mk_m0 = (m0 >= cf0) && (m0 < cf1), mk_m1 = (m0 + 1 >= cf0) && (m0 + 1 < cf1);
                     const bool mk_t0 = (tt0 >= ct0) && (tt0 < ct1), mk_t1 = (tt1 >= ct0) && (tt1 < ct1);
                     const bool ok_f0 = fl0 < nf, ok_f1 = fl0 + 8 < nf;
                     const bool ok_m0 = m0 < n_mels, ok_m1 = m0 + 1 < n_mels;
                     const int o00 = m0 * frames + tt0;
+                    float ls = 0.0f, lq = 0.0f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const bool ok = ((c & 2) ? ok_f1 : ok_f0) && ((c & 1) ? ok_m1 : ok_m0);
@@ -550,30 +622,43 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                             if (masked) v = 0.0f;
                             const int o = o00 + ((c & 1) ? frames : 0) + ((c & 2) ? 8 : 0);
                             out[o] = v;
-                            if (odb) odb[o] = v;
-                            if (omp) omp[o] = mp;
-                            const double dv = static_cast<double>(v);
-                            s_acc += dv;
-                            q_acc = fma(dv, dv, q_acc);
+                            if (EXTRA_OUT) {
+                                if (odb) odb[o] = v;
+                                if (omp) omp[o] = mp;
+                            }
+                            if (LM_F32_TILE_STATS) {
+                                ls += v;
+                                lq = fmaf(v, v, lq);
+                            } else {
+                                const double dv = static_cast<double>(v);
+                                s_acc += dv;
+                                q_acc = fma(dv, dv, q_acc);
+                            }
                         }
+                    }
+                    if (LM_F32_TILE_STATS) {
+                        s_acc += static_cast<double>(ls);
+                        q_acc += static_cast<double>(lq);
                     }
                 }
             }
+            s_stat[tid] = make_double2(s_acc, q_acc);
         }
 
-        // ---- gather part of the next item (its TMA part is already in flight) -----------------------------
-        if (has_next) stage_gather(&s_ctx[nslot], ntile, buf ^ 1);
+        // ---- gather part of item it+2 (its TMA part is already in flight) -----------------------------
+        if (has2) stage_gather(&s_ctx[ord2 & 3], tile2, buf);
 
         // ---- per-clip normalisation --------------------------------------------------------------------
-        if (!next_same_clip) {
+        if (tile + 1 == p.n_tiles) {
             if (p.normalize) {
                 float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+                double s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
                     q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
                 }
-                if (lane == 0) { red[warp] = s_acc; red[kWarps + warp] = q_acc; }
+                if (lane_ == 0) { red[warp_] = s_acc; red[kWarps + warp_] = q_acc; }
                 __syncthreads();   // also orders every thread's dB stores before the re-read below
                 if (tid == 0) {
                     double s = 0.0, q = 0.0;
@@ -600,12 +685,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 for (int i = (n4 << 2) + tid; i < static_cast<int>(clip_elems); i += kThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;
             }
-            s_acc = 0.0; q_acc = 0.0;
-            clip += gridDim.x;
-            cur ^= 1;
+            s_stat[tid] = make_double2(0.0, 0.0);
             tile = 0;
+            ++ord;
         } else {
-            tile += 1;
+            ++tile;
         }
     }
 }
