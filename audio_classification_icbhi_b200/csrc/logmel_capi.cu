@@ -52,6 +52,7 @@ struct lm_plan {
     float* d_window = nullptr;
     float2* d_tw = nullptr;
     float2* d_utw = nullptr;
+    float4* d_wphase = nullptr;
     float4* d_melw = nullptr;
     lm::MelTable* d_tab = nullptr;
     // host pipeline
@@ -65,7 +66,7 @@ namespace {
 int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_wphase); cudaFree(p->d_melw); cudaFree(p->d_tab);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -83,7 +84,7 @@ lm::KParams make_params(const lm_plan* p) {
     k.db_scale = static_cast<float>(static_cast<double>(p->db_mult) * 0.30102999566398119521);
     k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
     k.norm_eps = p->norm_eps;
-    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.melw = p->d_melw; k.mel_table = p->d_tab;
+    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.wphase = p->d_wphase; k.melw = p->d_melw; k.mel_table = p->d_tab;
     return k;
 }
 
@@ -250,6 +251,13 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
         utw[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
     }
 
+    std::vector<float4> wphase(32);
+    for (int l = 0; l < 32; ++l) {
+        const double p0 = two_pi * (2.0 * l) / p->n_fft, p1 = two_pi * (2.0 * l + 1.0) / p->n_fft;
+        wphase[l] = make_float4(static_cast<float>(cos(p0)), static_cast<float>(cos(p1)),
+                                static_cast<float>(sin(p0)), static_cast<float>(sin(p1)));
+    }
+
     auto up = [&](void** dst, const void* src, size_t bytes) -> int {
         LM_CUDA(cudaMalloc(dst, bytes));
         LM_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
@@ -259,6 +267,7 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     if ((rc = up(reinterpret_cast<void**>(&p->d_window), cfg->window, sizeof(float) * p->n_fft)) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tw), tw.data(), sizeof(float2) * tw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
+        (rc = up(reinterpret_cast<void**>(&p->d_wphase), wphase.data(), sizeof(float4) * wphase.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float4) * melw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab)))) {
         free_plan(p);

@@ -49,6 +49,12 @@
 #ifndef LM_F32_TILE_STATS
 #define LM_F32_TILE_STATS 0 // 1: per-thread per-tile sums in fp32, accumulated across tiles in fp64
 #endif
+#ifndef LM_WINCALC
+#define LM_WINCALC 0    // 1: Hann window by angle addition in registers (2 FFMA2 per pair) instead of 32 LDS.64
+#endif
+#ifndef LM_TW_P1
+#define LM_TW_P1 0      // 1: twiddle multiply before barrier X (in part 1) instead of after it
+#endif
 #ifndef LM_SPLIT
 #define LM_SPLIT 1    // 1: CTA barrier X between the two halves of the FFT; 0: before the FFT
 #endif
@@ -92,6 +98,7 @@ struct KParams {
     const float* __restrict__ window;   // [NFFT]
     const float2* __restrict__ tw;      // [32*32]  W1024^(n2*k1) = (cos, -sin), index k1*32+n2
     const float2* __restrict__ utw;     // [512]    (cos, sin)(2 pi k / 2048)
+    const float4* __restrict__ wphase;  // [32]     (cos p0, cos p1, sin p0, sin p1), p_j = 2 pi (2 lane + j) / n_fft
     const float4* __restrict__ melw;    // [n_dk][32 lanes]: fb/4 in mma B-fragment order
     const MelTable* __restrict__ mel_table;
 };
@@ -182,9 +189,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 //           separately; the LDS.128 reads hand the second FFT register pairs of neighbouring
 //           points, the layout its packed stages 1-4 want -- see gen_fft.py) + second radix-32 FFT.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_cfft1024_part1(lm_f2 (&z)[32]) { lm_fft32_aos(z); }
-__device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
-                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
+__device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
 #if LM_TW2
     // Twiddle W1024^(lane*k1), k1 = 4a + b, as the product of two table entries W^(4a*lane) * W^(b*lane):
     // 10 shared-memory loads instead of 31 (the shared-memory pipe is the tighter resource here, and
@@ -216,6 +221,14 @@ __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[
         z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-w.y, w.y), lm_mul2(z[k1], lm_bcast(w.x)));
     }
 #endif
+}
+__device__ __forceinline__ void warp_cfft1024_part1(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
+    lm_fft32_aos(z);
+    if (LM_TW_P1) warp_twiddle(z, tw, lane);
+}
+__device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
+                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
+    if (!LM_TW_P1) warp_twiddle(z, tw, lane);
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -240,6 +253,10 @@ __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[
     lm_fft32_soa(pr, pi, xr, xi);
 }
 
+// -0.5 cos(2 pi n/32) and 0.5 sin(2 pi n/32): the n1-dependent half of the window's angle addition
+__device__ constexpr float kWinCa[32] = {-5.000000000e-01f, -4.903926402e-01f, -4.619397663e-01f, -4.157348062e-01f, -3.535533906e-01f, -2.777851165e-01f, -1.913417162e-01f, -9.754516101e-02f, -3.061616998e-17f, 9.754516101e-02f, 1.913417162e-01f, 2.777851165e-01f, 3.535533906e-01f, 4.157348062e-01f, 4.619397663e-01f, 4.903926402e-01f, 5.000000000e-01f, 4.903926402e-01f, 4.619397663e-01f, 4.157348062e-01f, 3.535533906e-01f, 2.777851165e-01f, 1.913417162e-01f, 9.754516101e-02f, 9.184850994e-17f, -9.754516101e-02f, -1.913417162e-01f, -2.777851165e-01f, -3.535533906e-01f, -4.157348062e-01f, -4.619397663e-01f, -4.903926402e-01f};
+__device__ constexpr float kWinSa[32] = {0.000000000e+00f, 9.754516101e-02f, 1.913417162e-01f, 2.777851165e-01f, 3.535533906e-01f, 4.157348062e-01f, 4.619397663e-01f, 4.903926402e-01f, 5.000000000e-01f, 4.903926402e-01f, 4.619397663e-01f, 4.157348062e-01f, 3.535533906e-01f, 2.777851165e-01f, 1.913417162e-01f, 9.754516101e-02f, 6.123233996e-17f, -9.754516101e-02f, -1.913417162e-01f, -2.777851165e-01f, -3.535533906e-01f, -4.157348062e-01f, -4.619397663e-01f, -4.903926402e-01f, -5.000000000e-01f, -4.903926402e-01f, -4.619397663e-01f, -4.157348062e-01f, -3.535533906e-01f, -2.777851165e-01f, -1.913417162e-01f, -9.754516101e-02f};
+
 template <int NFFT>
 struct Geo {
     static constexpr int FPW = (NFFT == 2048) ? 1 : 2;   // frames per warp pass
@@ -257,7 +274,8 @@ struct Smem {
     static constexpr size_t kCtx = kRed + sizeof(double) * 2 * kWarps + 16;   // four ClipCtx slots (ordinal & 3)
     static constexpr size_t kTab = kCtx + 4 * 64;
     static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fp64 (sum, sumsq)
-    static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
+    static constexpr size_t kWph = kStat + sizeof(double) * 2 * kThreads;          // window phase table
+    static constexpr size_t kWin = kWph + sizeof(float4) * 32;
     static constexpr size_t kTw = kWin + sizeof(float) * NFFT;
     static constexpr size_t kUtw = kTw + sizeof(float2) * 1024;
     static constexpr size_t kScr = kUtw + ((NFFT == 2048) ? sizeof(float2) * 512 : 0);
@@ -319,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx);
     const MelTable* const s_tab = reinterpret_cast<const MelTable*>(smem_raw + L::kTab);
     double2* const s_stat = reinterpret_cast<double2*>(smem_raw + L::kStat);
+    float4* const s_wph = reinterpret_cast<float4*>(smem_raw + L::kWph);
     float* const s_win = reinterpret_cast<float*>(smem_raw + L::kWin);
     float2* const s_tw = reinterpret_cast<float2*>(smem_raw + L::kTw);
     float2* const s_utw = reinterpret_cast<float2*>(smem_raw + L::kUtw);
@@ -335,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     // ---- constants -> shared memory, once per (persistent) CTA -----------------------------
     for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 1024; i += kThreads) s_tw[i] = p.tw[i];
+    if (tid < 32) s_wph[tid] = p.wphase[tid];
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
     for (int i = tid; i < 32 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
@@ -454,12 +474,27 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             if (NFFT == 2048) {
                 const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
+#if LM_WINCALC
+                // hann[64 n1 + 2 lane + j] = 0.5 - 0.5 cos(2 pi n1/32 + phi_j): angle addition with the
+                // per-lane (cos phi_j, sin phi_j) pairs; the constants in n1 are literals
+                const float4 wp4 = s_wph[lane];
+                const lm_f2 CP = lm_pack(wp4.x, wp4.y), SP = lm_pack(wp4.z, wp4.w);
+                (void)w2;
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float2 v = s2[32 * n1 + lane];
+                    const float ca = kWinCa[n1], sa = kWinSa[n1];
+                    const lm_f2 w = lm_fma2(lm_bcast(ca), CP, lm_fma2(lm_bcast(sa), SP, lm_bcast(0.5f)));
+                    z[n1] = lm_mul2(lm_pack(v.x, v.y), w);
+                }
+#else
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const float2 v = s2[32 * n1 + lane];
                     const float2 w = w2[32 * n1 + lane];
                     z[n1] = lm_mul2(lm_pack(v.x, v.y), lm_pack(w.x, w.y));
                 }
+#endif
             } else {
                 // n_fft = 1024: two frames per warp as one complex signal z = a + i b
                 const float* __restrict__ sa = sb + (2 * warp) * hop;
@@ -470,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     z[n1] = lm_mul2(lm_pack(sa[32 * n1 + lane], sbb[32 * n1 + lane]), lm_bcast(w));
                 }
             }
-            warp_cfft1024_part1(z);
+            warp_cfft1024_part1(z, s_tw, lane);
         }
 #if LM_SPLIT
         __syncthreads();   // (X) every warp is done with the mel phase of the previous item (rows are

@@ -9,12 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "audio_classification_icbhi_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "split_always": ["-DLM_SPLIT=1", "-DLM_ALWAYS_ACTIVE=1"],
-    "split_always_st200": ["-DLM_SPLIT=1", "-DLM_ALWAYS_ACTIVE=1", "-DLM_STAGGER_NS=200"],
-    "split_always_st500": ["-DLM_SPLIT=1", "-DLM_ALWAYS_ACTIVE=1", "-DLM_STAGGER_NS=500"],
-    "split_always_tw2": ["-DLM_SPLIT=1", "-DLM_ALWAYS_ACTIVE=1", "-DLM_TW2=1"],
-    "always_st1000": ["-DLM_ALWAYS_ACTIVE=1", "-DLM_STAGGER_NS=1000"],
-    "always_st1500": ["-DLM_ALWAYS_ACTIVE=1", "-DLM_STAGGER_NS=1500"],
+    "ship": [],
+    "wincalc": ["-DLM_WINCALC=1"],
 }
 
 def build():
