@@ -12,6 +12,10 @@ Three flavours of the same forward transform (sign e^{-2 pi i nk/N}), natural or
       every butterfly is 2 FADD2 or 3 FFMA2 -- half the issue slots of the scalar flavour.
       Used for the first (lane-local) FFT, whose input arrives from shared memory as float2.
 
+  lm_fft32_aos_from2(lm_f2 z[32])
+      the same network minus its first stage: the kernel computes z[r] +- z[r+16] itself, fused
+      with the Hann window (hann[n + n_fft/2] = 1 - hann[n], so one window load serves both inputs).
+
   lm_fft32_soa(const lm_f2 pr[16], const lm_f2 pi[16], float xr[32], float xi[32])
       input pr[m] = (re x[2m], re x[2m+1]), pi[m] likewise -- what the LDS.128 reads of the
       32x32 transpose deliver.  In DIT order those two points share every twiddle of stages 1-4
@@ -101,14 +105,16 @@ def gen_scalar(n: int) -> str:
 
 
 # --------------------------------------------------------------------------------------
-def gen_aos(n: int) -> str:
-    """Packed complex (re, im) per register."""
+def gen_aos(n: int, first_stage: int = 1) -> str:
+    """Packed complex (re, im) per register.  first_stage = 2: z[] already holds the results of the
+    first butterfly stage (z[r] +- z[r + n/2] in place) -- the caller fused it with the window."""
     bits = n.bit_length() - 1
     out, ops, tmp = [], 0, 0
     emit = out.append
-    emit(f"LM_HD LM_INLINE void lm_fft{n}_aos(lm_f2 (&z)[{n}]) {{")
+    name = f"lm_fft{n}_aos" if first_stage == 1 else f"lm_fft{n}_aos_from{first_stage}"
+    emit(f"LM_HD LM_INLINE void {name}(lm_f2 (&z)[{n}]) {{")
     cur = [f"z[{bitrev(i, bits)}]" for i in range(n)]
-    for s in range(1, bits + 1):
+    for s in range(first_stage, bits + 1):
         m, half = 1 << s, 1 << (s - 1)
         for k in range(0, n, m):
             for j in range(half):
@@ -137,7 +143,7 @@ def gen_aos(n: int) -> str:
     for i in range(n):
         emit(f"  z[{i}] = {cur[i]};")
     emit("}")
-    emit(f"// lm_fft{n}_aos: {ops} packed f32x2 ops")
+    emit(f"// {name}: {ops} packed f32x2 ops")
     return "\n".join(out)
 
 
@@ -221,6 +227,8 @@ def main() -> None:
         print(gen_scalar(n))
     print()
     print(gen_aos(32))
+    print()
+    print(gen_aos(32, first_stage=2))
     print()
     print(gen_soa32())
 

@@ -45,14 +45,13 @@ struct lm_plan {
     int device = 0;
     int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
     int tile_f = 0, n_tiles = 0, ns = 0, n_dk = 0, fb_nnz = 0;
-    int sm_count = 0, max_ctas = 0, use_tma = 1;
+    int sm_count = 0, max_ctas = 0, use_tma = 1, stagger_ns = 2000;
     size_t smem_bytes = 0;
     float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
     // device constants
     float* d_window = nullptr;
     float2* d_tw = nullptr;
     float2* d_utw = nullptr;
-    float4* d_wphase = nullptr;
     float4* d_melw = nullptr;
     lm::MelTable* d_tab = nullptr;
     // host pipeline
@@ -66,7 +65,7 @@ namespace {
 int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_wphase); cudaFree(p->d_melw); cudaFree(p->d_tab);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -80,11 +79,11 @@ int free_plan(lm_plan* p) {
 lm::KParams make_params(const lm_plan* p) {
     lm::KParams k{};
     k.T = p->T; k.hop = p->hop; k.frames = p->frames; k.n_mels = p->n_mels; k.n_tiles = p->n_tiles;
-    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma;
+    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma; k.stagger_ns = p->stagger_ns;
     k.db_scale = static_cast<float>(static_cast<double>(p->db_mult) * 0.30102999566398119521);
     k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
     k.norm_eps = p->norm_eps;
-    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.wphase = p->d_wphase; k.melw = p->d_melw; k.mel_table = p->d_tab;
+    k.window = p->d_window; k.tw = p->d_tw; k.utw = p->d_utw; k.melw = p->d_melw; k.mel_table = p->d_tab;
     return k;
 }
 
@@ -182,10 +181,14 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     p->floor_db = cfg->db_multiplier * log10f(cfg->amin) - cfg->db_offset;
     p->sm_count = prop.multiProcessorCount;
 
-    // ---- banded filterbank as mma.sync B fragments (scaled by 1/4: the kernel produces 4 |X|^2) ----
+    // ---- banded filterbank as mma.sync A fragments (scaled by 1/4: the kernel produces 4 |X|^2) ----
     // Mel tile mt = filters [8mt, 8mt+8).  Its band starts at kb (first non-zero bin, rounded down to
-    // 4) and is walked in steps of 16 bins.  For step d, lane (g = lane/4, tg = lane%4) holds
-    // fb[kb + 16d + 4tg + {0,1,2,3}][8mt + g] -- the k-permutation the kernel's LDS.128 A loads use.
+    // 4) and is walked in steps of 16 bins = two MMA k-steps.  For step d and k-step s, lane
+    // (g = lane/4, tg = lane%4) holds one float4 = the A fragment (a0, a1, a2, a3) =
+    // (head w0, residual w0, head w1, residual w1) with w_j = fb[kb + 16d + 4tg + 2s + j][8mt + g]:
+    // MMA rows 0-7 carry the TF32 head (low 13 mantissa bits cleared), rows 8-15 the residual w - head
+    // (13 significant bits, of which the tensor core keeps 11), and the k-permutation matches the
+    // kernel's LDS.128 loads of the power rows.
     const int n_mt = (p->n_mels + 7) / 8;
     lm::MelTable tab{};
     std::vector<float4> melw;
@@ -196,6 +199,14 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     auto fbv = [&](int k, int m) -> float {
         return (k < p->n_freqs && m < p->n_mels) ? 0.25f * cfg->fb[static_cast<size_t>(k) * p->n_mels + m] : 0.0f;
     };
+    auto head = [](float w) -> float {
+        uint32_t u;
+        memcpy(&u, &w, 4);
+        u &= 0xffffe000u;
+        float h;
+        memcpy(&h, &u, 4);
+        return h;
+    };
     const int row_cap = (p->n_fft == 2048) ? lm::kRowFloats : (lm::kRowFloats - lm::kPbOff);
     for (int mt = 0; mt < n_mt; ++mt) {
         int lo = -1, hi = -1;
@@ -204,58 +215,58 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
                 if (fbv(k, 8 * mt + g) != 0.0f) { if (lo < 0) lo = k; hi = k; }
         int kb = 0, ndk = 0;
         if (lo >= 0) { kb = lo & ~3; ndk = (hi + 1 - kb + 15) / 16; }
+        while (ndk > 0 && kb > 0 && kb + 16 * ndk > row_cap) kb -= 4;   // keep the padded band inside the row
         if (kb + 16 * ndk > row_cap) { free_plan(p); return LM_ERR_FILTERBANK; }
-        tab.kb[mt] = kb; tab.ndk[mt] = ndk; tab.off[mt] = static_cast<int>(melw.size() / 32);
+        tab.kb[mt] = kb; tab.ndk[mt] = ndk; tab.off[mt] = static_cast<int>(melw.size() / 64);
         for (int d = 0; d < ndk; ++d)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int g = lane >> 2, tg = lane & 3, k0 = kb + 16 * d + 4 * tg, m = 8 * mt + g;
-                melw.push_back(make_float4(fbv(k0, m), fbv(k0 + 1, m), fbv(k0 + 2, m), fbv(k0 + 3, m)));
-            }
+            for (int s = 0; s < 2; ++s)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, tg = lane & 3, k0 = kb + 16 * d + 4 * tg + 2 * s, m = 8 * mt + g;
+                    const float w0 = fbv(k0, m), w1 = fbv(k0 + 1, m);
+                    melw.push_back(make_float4(head(w0), w0 - head(w0), head(w1), w1 - head(w1)));
+                }
     }
-    if (melw.empty()) melw.assign(32, make_float4(0.f, 0.f, 0.f, 0.f));
-    p->n_dk = static_cast<int>(melw.size() / 32);
+    if (melw.empty()) melw.assign(64, make_float4(0.f, 0.f, 0.f, 0.f));
+    p->n_dk = static_cast<int>(melw.size() / 64);
     if (p->n_dk > lm::kMaxDk) { free_plan(p); return LM_ERR_FILTERBANK; }
-    // longest-processing-time assignment of mel tiles to warps, balanced per scheduler (warp % 4)
+    // longest-processing-time assignment of mel tiles to the 8 warps of a group (both groups use the
+    // same table); warps 2s and 2s+1... of one scheduler are warp % 4, balanced too
     {
-        for (auto& w : tab.warp_tile) { w[0] = -1; w[1] = -1; }
+        for (auto& w : tab.warp_tile)
+            for (int& t : w) t = -1;
         std::vector<int> order(n_mt);
         for (int i = 0; i < n_mt; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return tab.ndk[a] > tab.ndk[b]; });
-        int load_w[lm::kWarps] = {0}, load_s[4] = {0, 0, 0, 0}, cnt_w[lm::kWarps] = {0};
+        int load_w[lm::kGroupWarps] = {0}, load_s[4] = {0, 0, 0, 0}, cnt_w[lm::kGroupWarps] = {0};
         for (int mt : order) {
             int best = -1;
-            for (int w = 0; w < lm::kWarps; ++w) {
-                if (cnt_w[w] >= 2) continue;
+            for (int w = 0; w < lm::kGroupWarps; ++w) {
+                if (cnt_w[w] >= lm::kTileSlots) continue;
                 if (best < 0) { best = w; continue; }
-                const int a = load_s[w & 3] * 64 + load_w[w] * 2 + cnt_w[w];
-                const int b = load_s[best & 3] * 64 + load_w[best] * 2 + cnt_w[best];
-                // fewest tiles first (spread), then lightest scheduler, then lightest warp
-                if (cnt_w[w] < cnt_w[best] || (cnt_w[w] == cnt_w[best] && a < b)) best = w;
+                const int a = load_w[w] * 64 + load_s[w & 3];
+                const int b = load_w[best] * 64 + load_s[best & 3];
+                // lightest warp first, then lightest scheduler
+                if (a < b) best = w;
             }
             tab.warp_tile[best][cnt_w[best]++] = mt;
-            load_w[best] += tab.ndk[mt] + 1;
-            load_s[best & 3] += tab.ndk[mt] + 1;
+            load_w[best] += tab.ndk[mt] + 4;      // a tile's fixed cost (setup + epilogue) is worth ~4 steps
+            load_s[best & 3] += tab.ndk[mt] + 4;
         }
     }
 
     // ---- twiddles ---------------------------------------------------------------------------
-    std::vector<float2> tw(1024), utw(512);
+    std::vector<float2> tw(32 * lm::kTwRows), utw(512);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int k1 = 0; k1 < 32; ++k1)
+    for (int r = 0; r < lm::kTwRows; ++r) {
+        const int k1 = r < 3 ? r + 1 : 4 * (r - 2);   // 1, 2, 3, 4, 8, ..., 28
         for (int n2 = 0; n2 < 32; ++n2) {
             const double a = two_pi * static_cast<double>(k1 * n2) / 1024.0;
-            tw[k1 * 32 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
+            tw[r * 32 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));
         }
+    }
     for (int k = 0; k < 512; ++k) {
         const double a = two_pi * static_cast<double>(k) / 2048.0;
         utw[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
-    }
-
-    std::vector<float4> wphase(32);
-    for (int l = 0; l < 32; ++l) {
-        const double p0 = two_pi * (2.0 * l) / p->n_fft, p1 = two_pi * (2.0 * l + 1.0) / p->n_fft;
-        wphase[l] = make_float4(static_cast<float>(cos(p0)), static_cast<float>(cos(p1)),
-                                static_cast<float>(sin(p0)), static_cast<float>(sin(p1)));
     }
 
     auto up = [&](void** dst, const void* src, size_t bytes) -> int {
@@ -267,7 +278,6 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     if ((rc = up(reinterpret_cast<void**>(&p->d_window), cfg->window, sizeof(float) * p->n_fft)) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tw), tw.data(), sizeof(float2) * tw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
-        (rc = up(reinterpret_cast<void**>(&p->d_wphase), wphase.data(), sizeof(float4) * wphase.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float4) * melw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab)))) {
         free_plan(p);
@@ -276,6 +286,10 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
 
     // ---- shared memory --------------------------------------------------------------------
     cudaError_t e;
+    {
+        const size_t want = (p->n_fft == 2048) ? lm::Smem<2048>::total(p->ns, p->n_dk) : lm::Smem<1024>::total(p->ns, p->n_dk);
+        if (want > prop.sharedMemPerBlockOptin) { free_plan(p); return LM_ERR_FILTERBANK; }
+    }
     if (p->n_fft == 2048) {
         p->smem_bytes = lm::Smem<2048>::total(p->ns, p->n_dk);
         e = cudaFuncSetAttribute(lm::logmel_kernel<2048, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -317,6 +331,7 @@ int lm_plan_info(const lm_plan* plan, lm_info* info) {
 int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!plan || !key) return LM_ERR_INVALID_ARG;
     if (!strcmp(key, "tma")) { plan->use_tma = value ? 1 : 0; return LM_OK; }
+    if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
 }

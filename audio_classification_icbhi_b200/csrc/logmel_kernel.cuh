@@ -1,31 +1,38 @@
 // logmel_kernel.cuh -- the fused log-mel kernel for sm_100a (B200).
 //
-// One persistent CTA per SM (16 warps).  A CTA takes whole clips (blockIdx.x, += gridDim.x) and
-// walks a flat list of work items (clip, tile); a tile is 16 frames (32 for n_fft = 1024).
-// Two CTA barriers per item: X sits in the MIDDLE of the FFT (before the transpose first touches
-// the power rows), Y after it.  A warp that finishes its share of the mel phase of item i therefore
-// runs straight into the register-only first half of the FFT of item i+1 while slower warps are
-// still on the tensor cores.  Per item:
+// One persistent CTA per SM, 16 warps = TWO INDEPENDENT GROUPS of 8 warps.  A group is a
+// "virtual CTA": it owns whole clips (virtual index = group * gridDim.x + blockIdx.x, stride
+// 2 * gridDim.x), walks their (clip, tile) items on its own, and synchronises only with itself
+// (named barrier 1 + group, mbarrier [group]).  The groups share the constant tables in shared
+// memory and nothing else.  Group 1 starts half an item late, so that one group's FFT phase
+// (FMA-pipe bound) overlaps the other's mel phase (tensor pipe + shared-memory loads + epilogue):
+// within a group every warp is in the same phase, and a CTA made of one group leaves each pipe idle
+// half of the time.
 //
-//   stage   (done TWO items ahead, into the buffer just consumed) the tile's samples -> shared memory,
-//           once per sample although every sample feeds 4 frames.  The contiguous interior of
-//           a plain clip is one cp.async.bulk (TMA, 1-D) completing on an mbarrier; whatever
-//           is left -- torch.stft's reflect padding, zero padding, and whole tiles of augmented
-//           clips -- goes through the gather path that does pad/crop
-//           (R/src/data/preprocessing.py:70-83), noise and roll (:85-93) as index arithmetic.
-//   FFT     one warp = one frame.  x Hann, 2048 real -> 1024 complex points held as
-//           32 registers/lane; register radix-32 FFT over the lane-local index, twiddle,
-//           32x32 transpose through the warp's shared-memory row, second radix-32 FFT,
-//           then the real-FFT untangle with the partner bin fetched by warp shuffle;
-//           4|X|^2 overwrites the warp's row (never HBM).
-//           (TA/functional/functional.py:123-145: torch.stft + abs().pow(2))
-//   mel     [16 frames x bins] . [bins x 8 mels] per warp on the tensor cores:
-//           mma.sync m16n8k8 TF32 with both operands split hi+lo (3 MMAs per step, error
-//           ~2^-22), walking only the band of bins the 8 filters touch
+// A tile is 8 frames (16 for n_fft = 1024); one warp = one frame.  Per item, inside a group:
+//
+//   stage   (one item ahead, into the group's single buffer as soon as every warp has pulled its
+//           frame into registers) the tile's samples -> shared memory, once per sample although
+//           every sample feeds 4 frames.  The contiguous interior of a plain clip is one
+//           cp.async.bulk (TMA, 1-D) completing on an mbarrier; whatever is left -- torch.stft's
+//           reflect padding, zero padding, and whole tiles of augmented clips -- goes through the
+//           gather path that does pad/crop (R/src/data/preprocessing.py:70-83), noise and roll
+//           (:85-93) as index arithmetic.
+//   FFT     x Hann fused with the first butterfly stage (hann[n + n_fft/2] = 1 - hann[n]: one
+//           window load per two samples), 2048 real -> 1024 complex points held as 32
+//           registers/lane; register radix-32 FFT over the lane-local index, twiddle, 32x32
+//           transpose through the warp's shared-memory row, second radix-32 FFT, then the real-FFT
+//           untangle with the partner bin fetched by warp shuffle; 4|X|^2 overwrites the warp's
+//           row (never HBM).  (TA/functional/functional.py:123-145: torch.stft + abs().pow(2))
+//   mel     on the tensor cores, filterbank-stationary: mma.sync m16n8k8 TF32 with
+//           A = [8 mels x {hi, lo}] x 8 bins (the 16 MMA rows hold the TF32 head and the residual
+//           of the same 8 filters), B = 8 bins x 8 frames of the power rows, once with the head
+//           and once with the residual of the power: 2 MMAs per 8 bins give all four partial
+//           products, error ~2^-19.  Only the band of bins the 8 filters touch is walked
 //           (TA/transforms/_transforms.py:417).  Epilogue in registers: 10*log10(max(x, amin))
 //           (TA/functional/functional.py:390-391), SpecAugment intervals (:939-953), store,
 //           fp64 sum / sum-of-squares.
-//   norm    when the clip is finished the same CTA re-reads its (L2-resident) dB block and
+//   norm    when the clip is finished the same group re-reads its (L2-resident) dB block and
 //           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116).
 //
 // Algorithmic HBM bytes per clip: 4*min(len, T) read + 4*n_mels*frames written.
@@ -36,44 +43,25 @@
 #include "../../include/logmel_b200.h"
 #include "fft_gen.cuh"
 
-// Build-time experiment switches (tools/build_variants.py); the defaults are the shipped kernel.
-#ifndef LM_TW2
-#define LM_TW2 1      // 1: twiddle = product of two table entries (10 loads); 0: 31 table loads
-#endif
-#ifndef LM_ALWAYS_ACTIVE
-#define LM_ALWAYS_ACTIVE 1   // 1: warps whose frame is past the clip end compute anyway (no divergent join)
-#endif
-#ifndef LM_STAGGER_NS
-#define LM_STAGGER_NS 0     // > 0: warps of one scheduler start the FFT (warp/4) * ns apart
-#endif
-#ifndef LM_F32_TILE_STATS
-#define LM_F32_TILE_STATS 0 // 1: per-thread per-tile sums in fp32, accumulated across tiles in fp64
-#endif
-#ifndef LM_WINCALC
-#define LM_WINCALC 0    // 1: Hann window by angle addition in registers (2 FFMA2 per pair) instead of 32 LDS.64
-#endif
-#ifndef LM_TW_P1
-#define LM_TW_P1 0      // 1: twiddle multiply before barrier X (in part 1) instead of after it
-#endif
-#ifndef LM_SPLIT
-#define LM_SPLIT 1    // 1: CTA barrier X between the two halves of the FFT; 0: before the FFT
-#endif
-
 namespace lm {
 
-constexpr int kWarps = 16;
+constexpr int kGroups = 2;
+constexpr int kGroupWarps = 8;
+constexpr int kGroupThreads = kGroupWarps * 32;
+constexpr int kWarps = kGroups * kGroupWarps;
 constexpr int kThreads = kWarps * 32;
 constexpr int kScrPitch = 36;                 // transpose rows: 32 + 4 (16 B aligned, LDS.128 conflict-free)
 constexpr int kRowFloats = 1168;              // per-warp row: >= 32*36 and == 16 (mod 32) for the MMA loads
 constexpr int kPbOff = 528;                   // n_fft=1024: second frame's spectrum inside the row (== 16 mod 32)
 constexpr int kMaxMelTiles = 32;              // n_mels <= 256
-constexpr int kMaxDk = 96;                    // 16-bin steps of banded filterbank kept on chip (48 KB)
+constexpr int kTileSlots = kMaxMelTiles / kGroupWarps;   // mel tiles per warp, at most
+constexpr int kMaxDk = 96;                    // 16-bin steps of banded filterbank kept on chip (1 KB each)
 
 struct MelTable {                             // lives in global memory, copied to shared
     int kb[kMaxMelTiles];                     // first bin of the tile's band (multiple of 4)
     int ndk[kMaxMelTiles];                    // 16-bin steps in the band
-    int off[kMaxMelTiles];                    // first step's index into melw (units of 32 float4)
-    int warp_tile[kWarps][2];                 // mel tiles owned by each warp (-1 = none)
+    int off[kMaxMelTiles];                    // first step's index into melw (units of 64 float4)
+    int warp_tile[kGroupWarps][kTileSlots];   // mel tiles owned by each warp of a group (-1 = none)
 };
 
 struct KParams {
@@ -93,18 +81,18 @@ struct KParams {
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
     int n_dk;        // total 16-bin steps in melw
     int use_tma;
+    int stagger_ns;  // head start of group 0 over group 1
     float db_scale;  // db_multiplier * log10(2): dB = db_scale * log2(x) - db_offset
     float amin, db_offset, floor_db, norm_eps;
-    const float* __restrict__ window;   // [NFFT]
-    const float2* __restrict__ tw;      // [32*32]  W1024^(n2*k1) = (cos, -sin), index k1*32+n2
+    const float* __restrict__ window;   // [NFFT] (the first half is used)
+    const float2* __restrict__ tw;      // [kTwRows*32]  W1024^(n2*k1) = (cos, -sin), rows k1 = 1,2,3,4,8,...,28
     const float2* __restrict__ utw;     // [512]    (cos, sin)(2 pi k / 2048)
-    const float4* __restrict__ wphase;  // [32]     (cos p0, cos p1, sin p0, sin p1), p_j = 2 pi (2 lane + j) / n_fft
-    const float4* __restrict__ melw;    // [n_dk][32 lanes]: fb/4 in mma B-fragment order
+    const float4* __restrict__ melw;    // [n_dk][2 k-steps][32 lanes]: mma A fragments (head, residual, head, residual)
     const MelTable* __restrict__ mel_table;
 };
 
 // ---------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk copy (TMA) global -> shared, TF32 mma
+// PTX helpers: mbarrier + 1-D bulk copy (TMA) global -> shared, named barrier, TF32 mma
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -141,6 +129,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// barrier of one 8-warp group (ids 1 and 2; id 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+}
 // D += A(16x8, row) * B(8x8, col), TF32 inputs (low 13 mantissa bits ignored), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -154,6 +146,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ int launder(int v) {
     asm volatile("" : "+r"(v));
     return v;
+}
+// log2 of a normal positive number: plain MUFU.LG2, no denormal pre-scaling (callers pass x > amin)
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
@@ -181,16 +179,17 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 1024-point complex FFT of one warp, in two halves so that a CTA barrier can sit between them.
-// On entry lane n2 holds z[32*n1 + n2] in z[n1] (re, im packed in one 64-bit register); on exit lane
+// 1024-point complex FFT of one warp, in two halves so that the group barrier can sit between them.
+// Lane n2 holds z[32*n1 + n2] in z[n1] (re, im packed in one 64-bit register); on exit lane
 // k1 holds Z[k1 + 32*k2] in (xr[k2], xi[k2]).
-//   part 1 (registers only): packed complex radix-32 FFT over the lane-local index;
+//   part 1 (registers only): packed complex radix-32 FFT over the lane-local index.  Its first
+//           butterfly stage (z[r] +- z[r+16]) is done by the caller, fused with the window.
 //   part 2: twiddle, 32x32 transpose through the warp's private row `scr` (real and imaginary planes
 //           separately; the LDS.128 reads hand the second FFT register pairs of neighbouring
 //           points, the layout its packed stages 1-4 want -- see gen_fft.py) + second radix-32 FFT.
 // ---------------------------------------------------------------------------------------
+constexpr int kTwRows = 10;   // twiddle table rows kept on chip: k1 = 1, 2, 3, 4, 8, 12, ..., 28
 __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
-#if LM_TW2
     // Twiddle W1024^(lane*k1), k1 = 4a + b, as the product of two table entries W^(4a*lane) * W^(b*lane):
     // 10 shared-memory loads instead of 31 (the shared-memory pipe is the tighter resource here, and
     // 31 loads in flight on top of z do not fit the register file), one extra rounding per twiddle.
@@ -198,37 +197,26 @@ __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __res
     auto cmul = [](lm_f2 v, lm_f2 w) {
         return lm_fma2(lm_swap(v), lm_pack(-lm_hi(w), lm_hi(w)), lm_mul2(v, lm_bcast(lm_lo(w))));
     };
-    auto ldtw = [&](int k1) {
-        const float2 w = tw[k1 * 32 + lane];
+    auto ldtw = [&](int row) {
+        const float2 w = tw[row * 32 + lane];
         return lm_pack(w.x, w.y);
     };
-    const lm_f2 B1 = ldtw(1), B2 = ldtw(2), B3 = ldtw(3);
+    const lm_f2 B1 = ldtw(0), B2 = ldtw(1), B3 = ldtw(2);
     z[1] = cmul(z[1], B1);
     z[2] = cmul(z[2], B2);
     z[3] = cmul(z[3], B3);
 #pragma unroll
     for (int a = 1; a < 8; ++a) {
-        const lm_f2 A = ldtw(4 * a);
+        const lm_f2 A = ldtw(2 + a);
         z[4 * a] = cmul(z[4 * a], A);
         z[4 * a + 1] = cmul(z[4 * a + 1], cmul(A, B1));
         z[4 * a + 2] = cmul(z[4 * a + 2], cmul(A, B2));
         z[4 * a + 3] = cmul(z[4 * a + 3], cmul(A, B3));
     }
-#else
-#pragma unroll
-    for (int k1 = 1; k1 < 32; ++k1) {
-        const float2 w = tw[k1 * 32 + lane];   // (cos, -sin): (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy)
-        z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-w.y, w.y), lm_mul2(z[k1], lm_bcast(w.x)));
-    }
-#endif
-}
-__device__ __forceinline__ void warp_cfft1024_part1(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
-    lm_fft32_aos(z);
-    if (LM_TW_P1) warp_twiddle(z, tw, lane);
 }
 __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
                                                     float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
-    if (!LM_TW_P1) warp_twiddle(z, tw, lane);
+    warp_twiddle(z, tw, lane);
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -253,42 +241,38 @@ __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[
     lm_fft32_soa(pr, pi, xr, xi);
 }
 
-// -0.5 cos(2 pi n/32) and 0.5 sin(2 pi n/32): the n1-dependent half of the window's angle addition
-__device__ constexpr float kWinCa[32] = {-5.000000000e-01f, -4.903926402e-01f, -4.619397663e-01f, -4.157348062e-01f, -3.535533906e-01f, -2.777851165e-01f, -1.913417162e-01f, -9.754516101e-02f, -3.061616998e-17f, 9.754516101e-02f, 1.913417162e-01f, 2.777851165e-01f, 3.535533906e-01f, 4.157348062e-01f, 4.619397663e-01f, 4.903926402e-01f, 5.000000000e-01f, 4.903926402e-01f, 4.619397663e-01f, 4.157348062e-01f, 3.535533906e-01f, 2.777851165e-01f, 1.913417162e-01f, 9.754516101e-02f, 9.184850994e-17f, -9.754516101e-02f, -1.913417162e-01f, -2.777851165e-01f, -3.535533906e-01f, -4.157348062e-01f, -4.619397663e-01f, -4.903926402e-01f};
-__device__ constexpr float kWinSa[32] = {0.000000000e+00f, 9.754516101e-02f, 1.913417162e-01f, 2.777851165e-01f, 3.535533906e-01f, 4.157348062e-01f, 4.619397663e-01f, 4.903926402e-01f, 5.000000000e-01f, 4.903926402e-01f, 4.619397663e-01f, 4.157348062e-01f, 3.535533906e-01f, 2.777851165e-01f, 1.913417162e-01f, 9.754516101e-02f, 6.123233996e-17f, -9.754516101e-02f, -1.913417162e-01f, -2.777851165e-01f, -3.535533906e-01f, -4.157348062e-01f, -4.619397663e-01f, -4.903926402e-01f, -5.000000000e-01f, -4.903926402e-01f, -4.619397663e-01f, -4.157348062e-01f, -3.535533906e-01f, -2.777851165e-01f, -1.913417162e-01f, -9.754516101e-02f};
-
 template <int NFFT>
 struct Geo {
     static constexpr int FPW = (NFFT == 2048) ? 1 : 2;   // frames per warp pass
-    static constexpr int TILE_F = kWarps * FPW;
-    static constexpr int MT = TILE_F / 16;               // 16-frame MMA row blocks per tile
+    static constexpr int TILE_F = kGroupWarps * FPW;     // frames per item
+    static constexpr int NB = TILE_F / 8;                // 8-frame MMA column blocks per tile
 };
 
 // Shared-memory carve-up, shared by host (size) and device (pointers).  Everything of fixed size
 // comes first so that its addresses are compile-time constants (no registers spent on pointers);
-// the two run-time sized arrays (staging buffers, filterbank) sit at the end.
+// the run-time sized arrays (staging buffers, filterbank) sit at the end.
 template <int NFFT>
 struct Smem {
-    static constexpr size_t kBar = 0;                                    // 2 mbarriers + 2 'TMA pending' flags
-    static constexpr size_t kRed = kBar + 32;                            // block-reduction scratch + broadcast
-    static constexpr size_t kCtx = kRed + sizeof(double) * 2 * kWarps + 16;   // four ClipCtx slots (ordinal & 3)
-    static constexpr size_t kTab = kCtx + 4 * 64;
+    static constexpr size_t kBar = 0;                                    // kGroups mbarriers + 'TMA pending' flags
+    static constexpr size_t kRed = kBar + 32;                            // per group: reduction scratch + broadcast
+    static constexpr size_t kRedGroup = sizeof(double) * 2 * kGroupWarps + 16;
+    static constexpr size_t kCtx = kRed + kGroups * kRedGroup;           // per group two ClipCtx slots (ordinal & 1)
+    static constexpr size_t kTab = kCtx + kGroups * 2 * 64;
     static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fp64 (sum, sumsq)
-    static constexpr size_t kWph = kStat + sizeof(double) * 2 * kThreads;          // window phase table
-    static constexpr size_t kWin = kWph + sizeof(float4) * 32;
-    static constexpr size_t kTw = kWin + sizeof(float) * NFFT;
-    static constexpr size_t kUtw = kTw + sizeof(float2) * 1024;
+    static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
+    static constexpr size_t kTw = kWin + sizeof(float) * (NFFT / 2);     // first half of the window
+    static constexpr size_t kUtw = kTw + sizeof(float2) * 32 * kTwRows;
     static constexpr size_t kScr = kUtw + ((NFFT == 2048) ? sizeof(float2) * 512 : 0);
     static constexpr size_t kSbuf = kScr + sizeof(float) * kWarps * kRowFloats;
-    static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0, "alignment");
-    static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * 2 * static_cast<size_t>(ns); }
+    static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0 && kRedGroup % 16 == 0, "alignment");
+    static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * kGroups * static_cast<size_t>(ns); }
     static __host__ __device__ size_t total(int ns, int n_dk) {
-        return melw_offset(ns) + sizeof(float4) * 32 * static_cast<size_t>(n_dk);
+        return melw_offset(ns) + sizeof(float4) * 64 * static_cast<size_t>(n_dk);
     }
 };
 
-// Everything the staging and epilogue code needs to know about one clip.  Four slots live in
-// shared memory (clip ordinal & 3: staging runs two items ahead of the epilogue) so that none of
+// Everything the staging and epilogue code needs to know about one clip.  Two slots per group live
+// in shared memory (clip ordinal & 1: staging runs one item ahead of the epilogue) so that none of
 // it occupies registers across the FFT.
 struct ClipCtx {
     const float* src;    // first sample after the centre crop
@@ -330,50 +314,52 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using L = Smem<NFFT>;
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + L::kBar);
-    volatile int* const s_pend = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 16);
-    double* const red = reinterpret_cast<double*>(smem_raw + L::kRed);
-    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + sizeof(double) * 2 * kWarps);
-    ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx);
+    const int tid = threadIdx.x, lane_ = tid & 31;
+    const int group = tid >> 8;                       // warp-uniform
+    const int gtid = tid & (kGroupThreads - 1), gwarp_ = gtid >> 5;
+
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + L::kBar) + group;
+    volatile int* const s_pend = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 16) + group;
+    double* const red = reinterpret_cast<double*>(smem_raw + L::kRed + group * L::kRedGroup);
+    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + group * L::kRedGroup + sizeof(double) * 2 * kGroupWarps);
+    ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx) + 2 * group;
     const MelTable* const s_tab = reinterpret_cast<const MelTable*>(smem_raw + L::kTab);
     double2* const s_stat = reinterpret_cast<double2*>(smem_raw + L::kStat);
-    float4* const s_wph = reinterpret_cast<float4*>(smem_raw + L::kWph);
     float* const s_win = reinterpret_cast<float*>(smem_raw + L::kWin);
     float2* const s_tw = reinterpret_cast<float2*>(smem_raw + L::kTw);
     float2* const s_utw = reinterpret_cast<float2*>(smem_raw + L::kUtw);
-    float* const scr_all = reinterpret_cast<float*>(smem_raw + L::kScr);
-    float* const sbuf = reinterpret_cast<float*>(smem_raw + L::kSbuf);
+    float* const rows = reinterpret_cast<float*>(smem_raw + L::kScr) + group * (kGroupWarps * kRowFloats);
+    float* const sb = reinterpret_cast<float*>(smem_raw + L::kSbuf) + static_cast<size_t>(group) * p.ns;
     float4* const s_melw = reinterpret_cast<float4*>(smem_raw + L::melw_offset(p.ns));
 
-    const int tid = threadIdx.x, lane_ = tid & 31, warp_ = tid >> 5;
-
-    const int n_my = (p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    if (n_my <= 0) return;
-    const int n_items = n_my * p.n_tiles;
-
-    // ---- constants -> shared memory, once per (persistent) CTA -----------------------------
-    for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
-    for (int i = tid; i < 1024; i += kThreads) s_tw[i] = p.tw[i];
-    if (tid < 32) s_wph[tid] = p.wphase[tid];
+    // ---- constants -> shared memory, once per (persistent) CTA, by all 16 warps -----------------
+    for (int i = tid; i < HALF; i += kThreads) s_win[i] = p.window[i];
+    for (int i = tid; i < 32 * kTwRows; i += kThreads) s_tw[i] = p.tw[i];
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
-    for (int i = tid; i < 32 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
+    for (int i = tid; i < 64 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
     for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
         reinterpret_cast<int*>(smem_raw + L::kTab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
-    for (int i = tid; i < kWarps * kRowFloats; i += kThreads) scr_all[i] = 0.0f;   // pad columns stay finite
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    for (int i = gtid; i < kGroupWarps * kRowFloats; i += kGroupThreads) rows[i] = 0.0f;   // pad columns stay finite
+    for (int i = gtid; i < p.ns; i += kGroupThreads) sb[i] = 0.0f;
+    if (gtid == 0) {
+        mbar_init(mbar, 1);
         fence_mbar_init();
-        s_pend[0] = 0;
-        s_pend[1] = 0;
+        *s_pend = 0;
     }
-    __syncthreads();
+    __syncthreads();   // the only CTA-wide barrier: from here on the groups never meet again
+
+    // ---- this group's clips -----------------------------------------------------------------------
+    const int nv = static_cast<int>(gridDim.x) * kGroups;
+    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+    const int n_my = (p.B - clip0 + nv - 1) / nv;
+    if (n_my <= 0) return;
+    const int n_items = n_my * p.n_tiles;
 
     const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
     const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
 
-    // ---- staging of one item into buffer `buf` -------------------------------------------------
+    // ---- staging of one item into the group's buffer -------------------------------------------------
     // bulk part: [e_lo, e_lo + cnt) of the tile is src[j0 + e_lo ...] verbatim (plain clips only)
     auto bulk_range = [&](const ClipCtx* __restrict__ c, int tile_, int& e_lo, int& cnt) {
         e_lo = 0; cnt = 0;
@@ -390,31 +376,31 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         e_lo = lo;
         cnt = (hi - lo) & ~3;
     };
-    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_, int buf) {   // ONE thread
+    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_) {   // ONE thread of the group
         int e_lo, cnt;
         bulk_range(c, tile_, e_lo, cnt);
         if (cnt != 0) {
             const int j0 = tile_ * TILE_F * hop - HALF;
             fence_proxy_async();
-            mbar_expect_tx(&mbar[buf], static_cast<uint32_t>(cnt) * 4u);
-            bulk_g2s(sbuf + static_cast<size_t>(buf) * p.ns + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u,
-                     &mbar[buf]);
+            mbar_expect_tx(mbar, static_cast<uint32_t>(cnt) * 4u);
+            bulk_g2s(sb + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u, mbar);
         }
-        s_pend[buf] = (cnt != 0);
+        *s_pend = (cnt != 0);
     };
-    auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_, int buf) {   // all threads
-        const ClipCtx c = *cc;
+    // returns (group-uniform) whether anything was written
+    auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_) -> bool {   // all threads of the group
         int e_lo, cnt;
         bulk_range(cc, tile_, e_lo, cnt);
+        const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
+        if (rest <= 0) return false;
+        const ClipCtx c = *cc;
         const int tf = tile_ * TILE_F;
         const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
         const int need = (nf - 1) * hop + NFFT;
         const int j0 = tf * hop - HALF;
-        float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
         // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
         // feed only frames >= `frames` and are zeroed
-        const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
-        for (int idx = tid; idx < rest; idx += kThreads) {
+        for (int idx = gtid; idx < rest; idx += kGroupThreads) {
             const int e = idx < e_lo ? idx : idx + cnt;
             int j = j0 + e;
             if (j < 0) j = -j;
@@ -432,90 +418,85 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             }
             sb[e] = v;
         }
+        return true;
     };
 
-    // ---- prologue: items 0 and 1 are staged before the loop; item it+2 is staged during item it ------
-    const int clip0 = blockIdx.x, cstride = gridDim.x;
-    if (tid == 0) {
+    // ---- prologue: item 0 is staged before the loop; item it+1 is staged during item it ----------------
+    const int cstride = nv;
+    if (gtid == 0) {
         load_clip(p, clip0, &s_ctx[0]);
-        if (p.n_tiles == 1 && n_items > 1) load_clip(p, clip0 + cstride, &s_ctx[1]);
-        stage_bulk(&s_ctx[0], 0, 0);
-        if (n_items > 1) stage_bulk(&s_ctx[p.n_tiles == 1 ? 1 : 0], p.n_tiles == 1 ? 0 : 1, 1);
+        stage_bulk(&s_ctx[0], 0);
     }
-    __syncthreads();
-    stage_gather(&s_ctx[0], 0, 0);
-    if (n_items > 1) stage_gather(&s_ctx[p.n_tiles == 1 ? 1 : 0], p.n_tiles == 1 ? 0 : 1, 1);
-    __syncthreads();
+    group_bar(group);
+    stage_gather(&s_ctx[0], 0);
+    group_bar(group);
+    if (group == 1 && p.stagger_ns > 0) {   // spin (nanosleep may return early): ~2 cycles per ns
+        const long long t_end = clock64() + 2LL * p.stagger_ns;
+        while (clock64() < t_end) {}
+    }
 
-    uint32_t parity0 = 0, parity1 = 0;     // mbarrier phase per staging buffer (CTA-uniform)
+    uint32_t parity = 0;                   // mbarrier phase of the staging buffer (group-uniform)
     s_stat[tid] = make_double2(0.0, 0.0);  // this thread's running (sum, sum of squares) of the clip's dB values
     int tile = 0, ord = 0;                 // tile index and clip ordinal of item `it`
 
 #pragma unroll 1
     for (int it = 0; it < n_items; ++it) {
-        const int buf = it & 1;
         const int tf = tile * TILE_F;                  // first frame of the tile
         const int clip = clip0 + ord * cstride;
-        const float* __restrict__ sb = sbuf + static_cast<size_t>(buf) * p.ns;
-        if (s_pend[buf]) {
-            mbar_wait(&mbar[buf], buf ? parity1 : parity0);
-            if (buf) parity1 ^= 1u; else parity0 ^= 1u;
+        if (*s_pend) {
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
         }
 
-#if !LM_SPLIT
-        __syncthreads();   // (X) placed before the FFT: experiment baseline
-#endif
-        // ---- FFT part 1 (registers + reads of the staged samples only) ----------------------------------
+        // ---- window + first butterfly stage + rest of FFT part 1 (registers; reads the staged samples) ----
+        // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
         lm_f2 z[32];
-        const bool active = LM_ALWAYS_ACTIVE ? true : ((NFFT == 2048) ? (tf + warp_ < frames) : (tf + 2 * warp_ < frames));
-        if (LM_STAGGER_NS > 0) __nanosleep((warp_ >> 2) * LM_STAGGER_NS);
-        if (active) {
-            const int lane = launder(lane_), warp = launder(warp_);
+        {
+            const int lane = launder(lane_), gw = launder(gwarp_);
             if (NFFT == 2048) {
-                const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + warp * hop);
+                const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + gw * hop);
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
-#if LM_WINCALC
-                // hann[64 n1 + 2 lane + j] = 0.5 - 0.5 cos(2 pi n1/32 + phi_j): angle addition with the
-                // per-lane (cos phi_j, sin phi_j) pairs; the constants in n1 are literals
-                const float4 wp4 = s_wph[lane];
-                const lm_f2 CP = lm_pack(wp4.x, wp4.y), SP = lm_pack(wp4.z, wp4.w);
-                (void)w2;
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float2 v = s2[32 * n1 + lane];
-                    const float ca = kWinCa[n1], sa = kWinSa[n1];
-                    const lm_f2 w = lm_fma2(lm_bcast(ca), CP, lm_fma2(lm_bcast(sa), SP, lm_bcast(0.5f)));
-                    z[n1] = lm_mul2(lm_pack(v.x, v.y), w);
+                for (int r = 0; r < 16; ++r) {
+                    const float2 v1 = s2[32 * r + lane];
+                    const float2 v2 = s2[32 * (r + 16) + lane];
+                    const float2 w = w2[32 * r + lane];
+                    const lm_f2 V1 = lm_pack(v1.x, v1.y), V2 = lm_pack(v2.x, v2.y), W = lm_pack(w.x, w.y);
+                    z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
+                    z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-v2.x, -v2.y));
                 }
-#else
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float2 v = s2[32 * n1 + lane];
-                    const float2 w = w2[32 * n1 + lane];
-                    z[n1] = lm_mul2(lm_pack(v.x, v.y), lm_pack(w.x, w.y));
-                }
-#endif
             } else {
                 // n_fft = 1024: two frames per warp as one complex signal z = a + i b
-                const float* __restrict__ sa = sb + (2 * warp) * hop;
+                const float* __restrict__ sa = sb + (2 * gw) * hop;
                 const float* __restrict__ sbb = sa + hop;
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float w = s_win[32 * n1 + lane];
-                    z[n1] = lm_mul2(lm_pack(sa[32 * n1 + lane], sbb[32 * n1 + lane]), lm_bcast(w));
+                for (int r = 0; r < 16; ++r) {
+                    const float a1 = sa[32 * r + lane], a2 = sa[32 * (r + 16) + lane];
+                    const float b1 = sbb[32 * r + lane], b2 = sbb[32 * (r + 16) + lane];
+                    const lm_f2 V1 = lm_pack(a1, b1), V2 = lm_pack(a2, b2), W = lm_bcast(s_win[32 * r + lane]);
+                    z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
+                    z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-a2, -b2));
                 }
             }
-            warp_cfft1024_part1(z, s_tw, lane);
+            lm_fft32_aos_from2(z);
         }
-#if LM_SPLIT
-        __syncthreads();   // (X) every warp is done with the mel phase of the previous item (rows are
-                           //     free) and with this item's staged samples (buffer `buf` is free)
-#endif
+        group_bar(group);   // (A) every warp of the group is done with the mel phase of the previous item
+                            //     (rows are free) and with this item's staged samples (buffer is free)
+
+        // ---- item it+1: its TMA part goes into the buffer just consumed; one thread; the clip's context
+        //      slot is filled when its first tile comes up ----------------------------------------------
+        const bool has1 = (it + 1 < n_items);
+        int tile1 = tile + 1, ord1 = ord;
+        if (tile1 == p.n_tiles) { tile1 = 0; ++ord1; }
+        if (has1 && gtid == 0) {
+            if (tile1 == 0) load_clip(p, clip0 + ord1 * cstride, &s_ctx[ord1 & 1]);
+            stage_bulk(&s_ctx[ord1 & 1], tile1);
+        }
 
         // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
-        if (active) {
-            const int lane = launder(lane_), warp = launder(warp_);
-            float* const scr = scr_all + warp * kRowFloats;
+        {
+            const int lane = launder(lane_), gw = launder(gwarp_);
+            float* const scr = rows + gw * kRowFloats;
             float xr[32], xi[32];
             warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane);
             const int srcl = (32 - lane) & 31;
@@ -583,105 +564,92 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 }
             }
         }
-        // ---- item it+2: its TMA part goes into the buffer consumed before (X).  Issued here, where no
-        //      FFT registers are live, by one thread; the clip's context slot is filled when its first
-        //      tile comes up. ------------------------------------------------------------------------------
-        const bool has2 = (it + 2 < n_items);
-        int tile2 = tile + 2, ord2 = ord;
-        while (tile2 >= p.n_tiles) { tile2 -= p.n_tiles; ++ord2; }
-        if (has2 && tid == 0) {
-            if (tile2 == 0) load_clip(p, clip0 + ord2 * cstride, &s_ctx[ord2 & 3]);
-            stage_bulk(&s_ctx[ord2 & 3], tile2, buf);
-        }
-        __syncthreads();   // (Y) all power rows of the tile are in shared memory
+        group_bar(group);   // (B) all power rows of the tile are in shared memory
 
-        // ---- mel phase: tensor cores, one 8-mel column block per warp ---------------------------------
+        // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
         {
-            const int lane = launder(lane_), warp = launder(warp_);
+            const int lane = launder(lane_), gw = launder(gwarp_);
             const int g = lane >> 2, tg = lane & 3;
             const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-            const ClipCtx* __restrict__ cx = &s_ctx[ord & 3];
-            double s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
+            const ClipCtx* __restrict__ cx = &s_ctx[ord & 1];
             float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
             float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
             float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+            const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
+            float ssum = 0.0f, qsum = 0.0f;   // fp32 over this item's (at most 4 NB kTileSlots) values, fp64 across items
 #pragma unroll 1
-            for (int slot = 0; slot < 2; ++slot) {
-                const int mt = s_tab->warp_tile[warp][slot];
+            for (int slot = 0; slot < kTileSlots; ++slot) {
+                const int mt = s_tab->warp_tile[gw][slot];
                 if (mt < 0) break;
                 const int kb = s_tab->kb[mt], ndk = s_tab->ndk[mt];
-                const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 32 + lane;
-#pragma unroll 1
-                for (int mb = 0; mb < G::MT; ++mb) {
-                    if (mb * 16 >= nf) break;
-                    // frame row f of the tile lives in warp row f/FPW (+ kPbOff for the odd frame)
-                    const int fa = mb * 16 + g, fb_ = fa + 8;
-                    const float* __restrict__ ra =
-                        scr_all + (fa / G::FPW) * kRowFloats + (fa % G::FPW) * kPbOff + kb + 4 * tg;
-                    const float* __restrict__ rb =
-                        scr_all + (fb_ / G::FPW) * kRowFloats + (fb_ % G::FPW) * kPbOff + kb + 4 * tg;
-                    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-                    for (int d = 0; d < ndk; ++d) {
-                        const float4 pa = *reinterpret_cast<const float4*>(ra + 16 * d);
-                        const float4 pb = *reinterpret_cast<const float4*>(rb + 16 * d);
-                        const float4 w = wp[32 * d];
-                        const uint32_t ah0 = tf32_hi(pa.x), ah1 = tf32_hi(pa.y), ah2 = tf32_hi(pa.z), ah3 = tf32_hi(pa.w);
-                        const uint32_t bh0 = tf32_hi(pb.x), bh1 = tf32_hi(pb.y), bh2 = tf32_hi(pb.z), bh3 = tf32_hi(pb.w);
-                        const uint32_t wh0 = tf32_hi(w.x), wh1 = tf32_hi(w.y), wh2 = tf32_hi(w.z), wh3 = tf32_hi(w.w);
-                        // k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
-                        mma_tf32(acc0, ah0, bh0, ah1, bh1, wh0, wh1);
-                        mma_tf32(acc1, tf32_lo(pa.x, ah0), tf32_lo(pb.x, bh0), tf32_lo(pa.y, ah1), tf32_lo(pb.y, bh1), wh0, wh1);
-                        mma_tf32(acc2, ah0, bh0, ah1, bh1, tf32_lo(w.x, wh0), tf32_lo(w.y, wh1));
-                        mma_tf32(acc0, ah2, bh2, ah3, bh3, wh2, wh3);
-                        mma_tf32(acc1, tf32_lo(pa.z, ah2), tf32_lo(pb.z, bh2), tf32_lo(pa.w, ah3), tf32_lo(pb.w, bh3), wh2, wh3);
-                        mma_tf32(acc2, ah2, bh2, ah3, bh3, tf32_lo(w.z, wh2), tf32_lo(w.w, wh3));
-                    }
-                    // epilogue: c0:(frame g, mel 2tg) c1:(g, 2tg+1) c2:(g+8, 2tg) c3:(g+8, 2tg+1)
-                    const int m0 = mt * 8 + 2 * tg, fl0 = mb * 16 + g;
-                    const int tt0 = tf + fl0, tt1 = tt0 + 8;
-                    const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
-                    const bool mk_m0 = (m0 >= cf0) && (m0 < cf1), mk_m1 = (m0 + 1 >= cf0) && (m0 + 1 < cf1);
-                    const bool mk_t0 = (tt0 >= ct0) && (tt0 < ct1), mk_t1 = (tt1 >= ct0) && (tt1 < ct1);
-                    const bool ok_f0 = fl0 < nf, ok_f1 = fl0 + 8 < nf;
-                    const bool ok_m0 = m0 < n_mels, ok_m1 = m0 + 1 < n_mels;
-                    const int o00 = m0 * frames + tt0;
-                    float ls = 0.0f, lq = 0.0f;
+                const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 64 + lane;
+                // B operand: frame n = g of column block nb lives in warp row (8 nb + g) / FPW
+                // (+ kPbOff for the odd frame); this lane reads bins kb + 16 d + 4 tg .. +3 of it
+                const float* rp[G::NB];
+                float acc_h[G::NB][4], acc_l[G::NB][4];   // products with the head / the residual of the power
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const bool ok = ((c & 2) ? ok_f1 : ok_f0) && ((c & 1) ? ok_m1 : ok_m0);
-                        if (ok) {
-                            const bool masked = ((c & 1) ? mk_m1 : mk_m0) || ((c & 2) ? mk_t1 : mk_t0);
-                            const float mp = acc0[c] + (acc1[c] + acc2[c]);
-                            float v = (mp <= p.amin) ? p.floor_db : fmaf(p.db_scale, __log2f(mp), -p.db_offset);
-                            if (masked) v = 0.0f;
-                            const int o = o00 + ((c & 1) ? frames : 0) + ((c & 2) ? 8 : 0);
-                            out[o] = v;
-                            if (EXTRA_OUT) {
-                                if (odb) odb[o] = v;
-                                if (omp) omp[o] = mp;
-                            }
-                            if (LM_F32_TILE_STATS) {
-                                ls += v;
-                                lq = fmaf(v, v, lq);
-                            } else {
-                                const double dv = static_cast<double>(v);
-                                s_acc += dv;
-                                q_acc = fma(dv, dv, q_acc);
-                            }
-                        }
-                    }
-                    if (LM_F32_TILE_STATS) {
-                        s_acc += static_cast<double>(ls);
-                        q_acc += static_cast<double>(lq);
+                for (int nb = 0; nb < G::NB; ++nb) {
+                    const int f = 8 * nb + g;
+                    rp[nb] = rows + (f / G::FPW) * kRowFloats + (f % G::FPW) * kPbOff + kb + 4 * tg;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { acc_h[nb][q] = 0.f; acc_l[nb][q] = 0.f; }
+                }
+#pragma unroll 2
+                for (int d = 0; d < ndk; ++d) {
+                    // A operand rows 0-7: TF32 head of fb[., mel g], rows 8-15: its residual; one LDS.128 is one
+                    // k-step's fragment.  k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
+                    const float4 w1 = wp[64 * d], w2 = wp[64 * d + 32];
+#pragma unroll
+                    for (int nb = 0; nb < G::NB; ++nb) {
+                        const float4 pv = *reinterpret_cast<const float4*>(rp[nb] + 16 * d);
+                        const uint32_t p0 = tf32_hi(pv.x), p1 = tf32_hi(pv.y), p2 = tf32_hi(pv.z), p3 = tf32_hi(pv.w);
+                        const lm_f2 r01 = lm_sub2(lm_pack(pv.x, pv.y), lm_pack(__uint_as_float(p0), __uint_as_float(p1)));
+                        const lm_f2 r23 = lm_sub2(lm_pack(pv.z, pv.w), lm_pack(__uint_as_float(p2), __uint_as_float(p3)));
+                        mma_tf32(acc_h[nb], __float_as_uint(w1.x), __float_as_uint(w1.y), __float_as_uint(w1.z), __float_as_uint(w1.w), p0, p1);
+                        mma_tf32(acc_l[nb], __float_as_uint(w1.x), __float_as_uint(w1.y), __float_as_uint(w1.z), __float_as_uint(w1.w),
+                                 __float_as_uint(lm_lo(r01)), __float_as_uint(lm_hi(r01)));
+                        mma_tf32(acc_h[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w), p2, p3);
+                        mma_tf32(acc_l[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w),
+                                 __float_as_uint(lm_lo(r23)), __float_as_uint(lm_hi(r23)));
                     }
                 }
+                // epilogue: c0:(head row, frame 2tg) c1:(head, 2tg+1) c2:(residual row, 2tg) c3:(residual, 2tg+1)
+                const int m = mt * 8 + g;
+                const bool ok_m = m < n_mels;
+                const bool mk_m = (m >= cf0) && (m < cf1);
+#pragma unroll
+                for (int nb = 0; nb < G::NB; ++nb) {
+                    const lm_f2 mp2 = lm_add2(lm_add2(lm_pack(acc_h[nb][0], acc_h[nb][1]), lm_pack(acc_h[nb][2], acc_h[nb][3])),
+                                              lm_add2(lm_pack(acc_l[nb][0], acc_l[nb][1]), lm_pack(acc_l[nb][2], acc_l[nb][3])));
+                    const int fl = 8 * nb + 2 * tg, tt = tf + fl;
+                    const int o = m * frames + tt;
+                    const float mp0 = lm_lo(mp2), mp1 = lm_hi(mp2);
+                    float v0 = (mp0 <= p.amin) ? p.floor_db : fmaf(p.db_scale, lg2_ftz(mp0), -p.db_offset);
+                    float v1 = (mp1 <= p.amin) ? p.floor_db : fmaf(p.db_scale, lg2_ftz(mp1), -p.db_offset);
+                    if (mk_m || ((tt >= ct0) && (tt < ct1))) v0 = 0.0f;
+                    if (mk_m || ((tt + 1 >= ct0) && (tt + 1 < ct1))) v1 = 0.0f;
+                    const bool ok0 = ok_m && (fl < nf), ok1 = ok_m && (fl + 1 < nf);
+                    if (ok0) out[o] = v0;
+                    if (ok1) out[o + 1] = v1;
+                    if (EXTRA_OUT) {
+                        if (odb) { if (ok0) odb[o] = v0; if (ok1) odb[o + 1] = v1; }
+                        if (omp) { if (ok0) omp[o] = mp0; if (ok1) omp[o + 1] = mp1; }
+                    }
+                    const float u0 = ok0 ? v0 : 0.0f, u1 = ok1 ? v1 : 0.0f;
+                    ssum += u0 + u1;
+                    qsum = fmaf(u0, u0, fmaf(u1, u1, qsum));
+                }
             }
-            s_stat[tid] = make_double2(s_acc, q_acc);
+            double2 st = s_stat[tid];
+            st.x += static_cast<double>(ssum);
+            st.y += static_cast<double>(qsum);
+            s_stat[tid] = st;
         }
 
-        // ---- gather part of item it+2 (its TMA part is already in flight) -----------------------------
-        if (has2) stage_gather(&s_ctx[ord2 & 3], tile2, buf);
+        // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
+        if (has1) {
+            if (stage_gather(&s_ctx[ord1 & 1], tile1)) group_bar(group);   // (C) only for tiles that touch a clip edge
+        }
 
         // ---- per-clip normalisation --------------------------------------------------------------------
         if (tile + 1 == p.n_tiles) {
@@ -693,11 +661,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
                     q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
                 }
-                if (lane_ == 0) { red[warp_] = s_acc; red[kWarps + warp_] = q_acc; }
-                __syncthreads();   // also orders every thread's dB stores before the re-read below
-                if (tid == 0) {
+                if (lane_ == 0) { red[gwarp_] = s_acc; red[kGroupWarps + gwarp_] = q_acc; }
+                group_bar(group);   // also orders every thread's dB stores before the re-read below
+                if (gtid == 0) {
                     double s = 0.0, q = 0.0;
-                    for (int w = 0; w < kWarps; ++w) { s += red[w]; q += red[kWarps + w]; }
+                    for (int w = 0; w < kGroupWarps; ++w) { s += red[w]; q += red[kGroupWarps + w]; }
                     const double n = static_cast<double>(clip_elems);
                     const double mean = s / n;
                     double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
@@ -705,11 +673,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     bcast[0] = static_cast<float>(mean);
                     bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
                 }
-                __syncthreads();
+                group_bar(group);
                 const float mean = bcast[0], inv = 1.0f / bcast[1];
                 float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
                 const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
-                for (int i = tid; i < n4; i += kThreads) {
+                for (int i = gtid; i < n4; i += kGroupThreads) {
                     float4 v = __ldcg(o4 + i);
                     v.x = (v.x - mean) * inv;
                     v.y = (v.y - mean) * inv;
@@ -717,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     v.w = (v.w - mean) * inv;
                     o4[i] = v;
                 }
-                for (int i = (n4 << 2) + tid; i < static_cast<int>(clip_elems); i += kThreads)
+                for (int i = (n4 << 2) + gtid; i < static_cast<int>(clip_elems); i += kGroupThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;
             }
             s_stat[tid] = make_double2(0.0, 0.0);

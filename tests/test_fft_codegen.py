@@ -16,6 +16,7 @@ HARNESS = r"""
 extern "C" void fft32(float* re, float* im){ float a[32], b[32]; for(int i=0;i<32;i++){a[i]=re[i];b[i]=im[i];} lm_fft32(a,b); for(int i=0;i<32;i++){re[i]=a[i];im[i]=b[i];} }
 extern "C" void fft16(float* re, float* im){ float a[16], b[16]; for(int i=0;i<16;i++){a[i]=re[i];b[i]=im[i];} lm_fft16(a,b); for(int i=0;i<16;i++){re[i]=a[i];im[i]=b[i];} }
 extern "C" void fft32_aos(float* re, float* im){ lm_f2 z[32]; for(int i=0;i<32;i++) z[i]=lm_pack(re[i],im[i]); lm_fft32_aos(z); for(int i=0;i<32;i++){re[i]=lm_lo(z[i]);im[i]=lm_hi(z[i]);} }
+extern "C" void fft32_aos_from2(float* re, float* im){ lm_f2 z[32]; for(int r=0;r<16;r++){ lm_f2 a=lm_pack(re[r],im[r]), b=lm_pack(re[r+16],im[r+16]); z[r]=lm_add2(a,b); z[r+16]=lm_sub2(a,b);} lm_fft32_aos_from2(z); for(int i=0;i<32;i++){re[i]=lm_lo(z[i]);im[i]=lm_hi(z[i]);} }
 extern "C" void fft32_soa(float* re, float* im){ lm_f2 pr[16], pi[16]; for(int m=0;m<16;m++){ pr[m]=lm_pack(re[2*m],re[2*m+1]); pi[m]=lm_pack(im[2*m],im[2*m+1]); } float a[32], b[32]; lm_fft32_soa(pr,pi,a,b); for(int i=0;i<32;i++){re[i]=a[i];im[i]=b[i];} }
 """
 
@@ -35,7 +36,8 @@ def test_generated_header_is_current():
     assert out == open(os.path.join(CSRC, "fft_gen.cuh")).read(), "run gen_fft.py > fft_gen.cuh"
 
 
-@pytest.mark.parametrize("name,n", [("fft16", 16), ("fft32", 32), ("fft32_aos", 32), ("fft32_soa", 32)])
+@pytest.mark.parametrize("name,n", [("fft16", 16), ("fft32", 32), ("fft32_aos", 32), ("fft32_aos_from2", 32),
+                                    ("fft32_soa", 32)])
 def test_fft_matches_numpy(harness, name, n):
     f = getattr(harness, name)
     p = ctypes.POINTER(ctypes.c_float)
@@ -58,9 +60,10 @@ def test_packed_and_scalar_flavours_agree_bitwise_enough(harness):
     rs = np.random.RandomState(3)
     x = rs.standard_normal(32) + 1j * rs.standard_normal(32)
     outs = []
-    for name in ("fft32", "fft32_aos", "fft32_soa"):
+    for name in ("fft32", "fft32_aos", "fft32_soa", "fft32_aos_from2"):
         re, im = x.real.astype(np.float32), x.imag.astype(np.float32)
         getattr(harness, name)(re.ctypes.data_as(p), im.ctypes.data_as(p))
         outs.append(re + 1j * im)
     np.testing.assert_array_equal(outs[0], outs[1])
     np.testing.assert_array_equal(outs[0], outs[2])
+    np.testing.assert_array_equal(outs[0], outs[3])
