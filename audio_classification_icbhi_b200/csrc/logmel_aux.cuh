@@ -85,4 +85,31 @@ __global__ void pcm16_roundtrip_kernel(const float* __restrict__ in, float* __re
     }
 }
 
+// 16-bit PCM -> fp32: x / 32768 (exact), what torchaudio.load(normalize=True) hands the reference for a
+// PCM_16 wav (R/src/data/preprocessing.py:57).  Eight samples per thread per pass: one 128-bit load, two
+// 128-bit stores; `in` and `out` must be 16-byte aligned, the tail is done element-wise.
+__global__ void pcm16_decode_kernel(const int16_t* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long n8 = n >> 3;
+    const int4* __restrict__ in8 = reinterpret_cast<const int4*>(in);
+    float4* __restrict__ out4 = reinterpret_cast<float4*>(out);
+    constexpr float k = 1.0f / 32768.0f;
+    for (long long i = tid; i < n8; i += stride) {
+        const int4 v = __ldcs(in8 + i);
+        float4 a, b;
+        a.x = static_cast<float>(static_cast<short>(v.x & 0xffff)) * k;
+        a.y = static_cast<float>(v.x >> 16) * k;
+        a.z = static_cast<float>(static_cast<short>(v.y & 0xffff)) * k;
+        a.w = static_cast<float>(v.y >> 16) * k;
+        b.x = static_cast<float>(static_cast<short>(v.z & 0xffff)) * k;
+        b.y = static_cast<float>(v.z >> 16) * k;
+        b.z = static_cast<float>(static_cast<short>(v.w & 0xffff)) * k;
+        b.w = static_cast<float>(v.w >> 16) * k;
+        out4[2 * i] = a;
+        out4[2 * i + 1] = b;
+    }
+    for (long long i = (n8 << 3) + tid; i < n; i += stride) out[i] = static_cast<float>(in[i]) * k;
+}
+
 }  // namespace lm

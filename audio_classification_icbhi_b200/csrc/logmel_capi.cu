@@ -32,10 +32,14 @@ constexpr int kSlots = 3;   // host pipeline depth
 struct HostSlot {
     cudaStream_t stream = nullptr;
     float* d_wave = nullptr;      size_t cap_wave = 0;     // floats
+    int16_t* d_pcm = nullptr;     size_t cap_pcm = 0;      // 16-bit samples (lm_forward_host_pcm16)
     float* d_noise = nullptr;     size_t cap_noise = 0;
     float* d_out = nullptr;       size_t cap_out = 0;
-    long long* d_off = nullptr;   int* d_len = nullptr;   lm_aug* d_aug = nullptr;
-    long long* h_off = nullptr;   // pinned
+    // per-chunk metadata, one pinned staging block and one device block: [offset int64 x n][aug 40 B x n][length int32 x n]
+    // (a copy from the caller's pageable arrays would make cudaMemcpyAsync wait for the stream, i.e. for the
+    //  chunk's waveform copy, and stall the pipeline once per chunk)
+    unsigned char* d_meta = nullptr;
+    unsigned char* h_meta = nullptr;   // pinned
     int cap_clips = 0;
 };
 
@@ -45,7 +49,8 @@ struct lm_plan {
     int device = 0;
     int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
     int tile_f = 0, n_tiles = 0, ns = 0, n_dk = 0, fb_nnz = 0;
-    int sm_count = 0, max_ctas = 0, use_tma = 1, stagger_ns = 2000;
+    int sm_count = 0, max_ctas = 0, use_tma = 1, stagger_ns = 0;
+    int host_chunk_clips = 0;   // lm_forward_host chunk size; 0 = automatic
     size_t smem_bytes = 0;
     float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
     // device constants
@@ -68,9 +73,9 @@ int free_plan(lm_plan* p) {
     cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
-        cudaFree(s.d_wave); cudaFree(s.d_noise); cudaFree(s.d_out);
-        cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_aug);
-        if (s.h_off) cudaFreeHost(s.h_off);
+        cudaFree(s.d_wave); cudaFree(s.d_pcm); cudaFree(s.d_noise); cudaFree(s.d_out);
+        cudaFree(s.d_meta);
+        if (s.h_meta) cudaFreeHost(s.h_meta);
     }
     delete p;
     return LM_OK;
@@ -312,6 +317,14 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
 
 int lm_plan_destroy(lm_plan* plan) { return free_plan(plan); }
 
+#if LM_TIMING
+// debug builds only (tools/build_variants.py "timing"): per-warp phase cycle counters of the last launch
+int lm_debug_timing(long long* host_out, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_out, lm::g_timing, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
+}
+#endif
+
 int lm_plan_frames(const lm_plan* plan) { return plan ? plan->frames : LM_ERR_INVALID_ARG; }
 
 int lm_plan_info(const lm_plan* plan, lm_info* info) {
@@ -331,6 +344,7 @@ int lm_plan_info(const lm_plan* plan, lm_info* info) {
 int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!plan || !key) return LM_ERR_INVALID_ARG;
     if (!strcmp(key, "tma")) { plan->use_tma = value ? 1 : 0; return LM_OK; }
+    if (!strcmp(key, "host_chunk_clips")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->host_chunk_clips = value; return LM_OK; }
     if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
@@ -374,9 +388,37 @@ int lm_pcm16_roundtrip(const float* in, float* out, int64_t n, void* cuda_stream
     return LM_OK;
 }
 
+int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream) {
+    if (n < 0) return LM_ERR_INVALID_ARG;
+    if (n == 0) return LM_OK;
+    if (!in || !out || (reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return LM_ERR_INVALID_ARG;
+    const int blocks = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256 + 1, 148 * 8));
+    lm::pcm16_decode_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, out, n);
+    LM_CUDA(cudaGetLastError());
+    return LM_OK;
+}
+
+static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, int64_t total_samples, const int64_t* offset,
+                             const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
+                             int32_t normalize);
+
 int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, const int64_t* offset,
                     const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
                     int32_t normalize) {
+    return forward_host_impl(plan, wave, false, total_samples, offset, length, B, aug, noise, out, normalize);
+}
+
+int lm_forward_host_pcm16(lm_plan* plan, const int16_t* pcm, int64_t total_samples, const int64_t* offset,
+                          const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
+                          int32_t normalize) {
+    return forward_host_impl(plan, pcm, true, total_samples, offset, length, B, aug, noise, out, normalize);
+}
+
+static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, int64_t total_samples, const int64_t* offset,
+                             const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
+                             int32_t normalize) {
+    const float* wave = static_cast<const float*>(wave_any);
+    const int16_t* pcm = static_cast<const int16_t*>(wave_any);
     if (!plan || B < 0 || total_samples < 0) return LM_ERR_INVALID_ARG;
     if (B == 0) return LM_OK;
     if (!wave || !offset || !length || !out) return LM_ERR_INVALID_ARG;
@@ -390,8 +432,8 @@ int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, con
 
     const size_t clip_elems = static_cast<size_t>(plan->n_mels) * plan->frames;
     // chunk so that a few chunks are in flight: ~64 MB of waveform, at least 2 SM-waves of clips
-    const int chunk = std::max(1, std::min<int>(B, std::max(2 * plan->sm_count,
-                                                            static_cast<int>((64u << 20) / (4u * static_cast<size_t>(plan->T))))));
+    const int auto_chunk = std::max(2 * plan->sm_count, static_cast<int>((64u << 20) / (4u * static_cast<size_t>(plan->T))));
+    const int chunk = std::max(1, std::min<int>(B, plan->host_chunk_clips > 0 ? plan->host_chunk_clips : auto_chunk));
     int slot_i = 0;
     for (int c0 = 0; c0 < B && rc == LM_OK; c0 += chunk, slot_i = (slot_i + 1) % kSlots) {
         const int n = std::min(chunk, B - c0);
@@ -404,36 +446,50 @@ int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, con
             hi = std::max(hi, offset[i] + length[i]);
         }
         if (lo == INT64_MAX) { lo = 0; hi = 0; }
-        lo &= ~int64_t(3);   // keep 16-byte alignment of clip starts (TMA staging path)
+        lo &= ~int64_t(7);   // keep 16-byte alignment of clip starts (TMA staging path; 8 PCM samples per int4)
         const size_t n_wave = static_cast<size_t>(hi - lo);
+        constexpr size_t kMetaPerClip = sizeof(long long) + sizeof(lm_aug) + sizeof(int);
         if (n > s.cap_clips) {
-            cudaFree(s.d_off); cudaFree(s.d_len); cudaFree(s.d_aug);
-            if (s.h_off) cudaFreeHost(s.h_off);
-            s.d_off = nullptr; s.d_len = nullptr; s.d_aug = nullptr; s.h_off = nullptr; s.cap_clips = 0;
-            if (cudaMalloc(&s.d_off, sizeof(long long) * n) != cudaSuccess ||
-                cudaMalloc(&s.d_len, sizeof(int) * n) != cudaSuccess ||
-                cudaMalloc(&s.d_aug, sizeof(lm_aug) * n) != cudaSuccess ||
-                cudaMallocHost(&s.h_off, sizeof(long long) * n) != cudaSuccess) {
+            cudaFree(s.d_meta);
+            if (s.h_meta) cudaFreeHost(s.h_meta);
+            s.d_meta = nullptr; s.h_meta = nullptr; s.cap_clips = 0;
+            if (cudaMalloc(&s.d_meta, kMetaPerClip * n) != cudaSuccess || cudaMallocHost(&s.h_meta, kMetaPerClip * n) != cudaSuccess) {
                 rc = cuda_fail(cudaGetLastError(), "slot metadata alloc");
                 break;
             }
             s.cap_clips = n;
         }
-        if ((rc = grow(&s.d_wave, &s.cap_wave, std::max<size_t>(n_wave + 4, 16)))) break;
+        // the blocks are laid out for the slot's capacity so that the three arrays keep their alignment
+        const size_t cap = static_cast<size_t>(s.cap_clips);
+        long long* h_off = reinterpret_cast<long long*>(s.h_meta);
+        lm_aug* h_aug = reinterpret_cast<lm_aug*>(s.h_meta + sizeof(long long) * cap);
+        int* h_len = reinterpret_cast<int*>(s.h_meta + (sizeof(long long) + sizeof(lm_aug)) * cap);
+        const long long* d_off = reinterpret_cast<const long long*>(s.d_meta);
+        const lm_aug* d_aug = reinterpret_cast<const lm_aug*>(s.d_meta + sizeof(long long) * cap);
+        const int* d_len = reinterpret_cast<const int*>(s.d_meta + (sizeof(long long) + sizeof(lm_aug)) * cap);
+        if ((rc = grow(&s.d_wave, &s.cap_wave, std::max<size_t>(n_wave + 8, 16)))) break;
+        if (pcm16 && (rc = grow(&s.d_pcm, &s.cap_pcm, std::max<size_t>(n_wave + 8, 16)))) break;
         if ((rc = grow(&s.d_out, &s.cap_out, clip_elems * n))) break;
         if (noise && (rc = grow(&s.d_noise, &s.cap_noise, static_cast<size_t>(plan->T) * n))) break;
-        for (int i = 0; i < n; ++i) s.h_off[i] = length[c0 + i] ? offset[c0 + i] - lo : 0;
+        for (int i = 0; i < n; ++i) h_off[i] = length[c0 + i] ? offset[c0 + i] - lo : 0;
+        memcpy(h_len, length + c0, sizeof(int) * n);
+        if (aug) memcpy(h_aug, aug + c0, sizeof(lm_aug) * n);
 
-        cudaError_t e = cudaSuccess;
-        if (n_wave) e = cudaMemcpyAsync(s.d_wave, wave + lo, sizeof(float) * n_wave, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_off, s.h_off, sizeof(long long) * n, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_len, length + c0, sizeof(int) * n, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess && aug) e = cudaMemcpyAsync(s.d_aug, aug + c0, sizeof(lm_aug) * n, cudaMemcpyHostToDevice, s.stream);
+        cudaError_t e = cudaMemcpyAsync(s.d_meta, s.h_meta, kMetaPerClip * cap, cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy (metadata)"); break; }
+        if (n_wave && !pcm16) e = cudaMemcpyAsync(s.d_wave, wave + lo, sizeof(float) * n_wave, cudaMemcpyHostToDevice, s.stream);
+        if (n_wave && pcm16) {
+            e = cudaMemcpyAsync(s.d_pcm, pcm + lo, sizeof(int16_t) * n_wave, cudaMemcpyHostToDevice, s.stream);
+            if (e == cudaSuccess) {
+                if ((rc = lm_pcm16_decode(s.d_pcm, s.d_wave, static_cast<int64_t>(n_wave), s.stream))) break;
+                ++plan->launches;
+            }
+        }
         if (e == cudaSuccess && noise)
             e = cudaMemcpyAsync(s.d_noise, noise + static_cast<size_t>(c0) * plan->T, sizeof(float) * plan->T * n,
                                 cudaMemcpyHostToDevice, s.stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
-        rc = launch(plan, s.d_wave, reinterpret_cast<const int64_t*>(s.d_off), s.d_len, n, aug ? s.d_aug : nullptr,
+        rc = launch(plan, s.d_wave, reinterpret_cast<const int64_t*>(d_off), d_len, n, aug ? d_aug : nullptr,
                     noise ? s.d_noise : nullptr, s.d_out, nullptr, nullptr, normalize, s.stream);
         if (rc) break;
         e = cudaMemcpyAsync(out + clip_elems * c0, s.d_out, sizeof(float) * clip_elems * n, cudaMemcpyDeviceToHost, s.stream);

@@ -43,7 +43,27 @@
 #include "../../include/logmel_b200.h"
 #include "fft_gen.cuh"
 
+// Build-time experiment switches (tools/build_variants.py); the shipped kernel is LM_EXP=0, LM_TIMING=0.
+//   LM_EXP     1: no mel phase (FFT only)   2: no FFT (mel phase on stale rows)   3: no FFT part 2
+//   LM_TIMING  1: every warp accumulates clock64() deltas per phase into lm::g_timing[block][warp][8]
+//              (read back with lm_debug_timing)
+#ifndef LM_EXP
+#define LM_EXP 0
+#endif
+#ifndef LM_TIMING
+#define LM_TIMING 0
+#endif
+#if LM_TIMING
+#define LM_T(slot) do { const long long t_now_ = clock64(); t_acc[slot] += t_now_ - t_last; t_last = t_now_; } while (0)
+#else
+#define LM_T(slot) do { } while (0)
+#endif
+
 namespace lm {
+
+#if LM_TIMING
+__device__ long long g_timing[160 * 16 * 8];
+#endif
 
 constexpr int kGroups = 2;
 constexpr int kGroupWarps = 8;
@@ -439,6 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     s_stat[tid] = make_double2(0.0, 0.0);  // this thread's running (sum, sum of squares) of the clip's dB values
     int tile = 0, ord = 0;                 // tile index and clip ordinal of item `it`
 
+#if LM_TIMING
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
+#endif
 #pragma unroll 1
     for (int it = 0; it < n_items; ++it) {
         const int tf = tile * TILE_F;                  // first frame of the tile
@@ -447,11 +471,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
         }
+        LM_T(0);   // staging wait
 
         // ---- window + first butterfly stage + rest of FFT part 1 (registers; reads the staged samples) ----
         // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
         lm_f2 z[32];
-        {
+        if (LM_EXP != 2) {
             const int lane = launder(lane_), gw = launder(gwarp_);
             if (NFFT == 2048) {
                 const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + gw * hop);
@@ -480,9 +505,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             }
             lm_fft32_aos_from2(z);
         }
+        LM_T(1);   // FFT part 1
         group_bar(group);   // (A) every warp of the group is done with the mel phase of the previous item
                             //     (rows are free) and with this item's staged samples (buffer is free)
 
+        LM_T(2);   // barrier A
         // ---- item it+1: its TMA part goes into the buffer just consumed; one thread; the clip's context
         //      slot is filled when its first tile comes up ----------------------------------------------
         const bool has1 = (it + 1 < n_items);
@@ -494,7 +521,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }
 
         // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
-        {
+        if (LM_EXP == 3) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += lm_lo(z[k]) + lm_hi(z[k]);
+            rows[gwarp_ * kRowFloats + lane_] = acc;
+        }
+        if (LM_EXP != 2 && LM_EXP != 3) {
             const int lane = launder(lane_), gw = launder(gwarp_);
             float* const scr = rows + gw * kRowFloats;
             float xr[32], xi[32];
@@ -564,7 +597,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 }
             }
         }
+        LM_T(3);   // FFT part 2 (+ TMA issue)
         group_bar(group);   // (B) all power rows of the tile are in shared memory
+        LM_T(4);   // barrier B
 
         // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
         {
@@ -580,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 #pragma unroll 1
             for (int slot = 0; slot < kTileSlots; ++slot) {
                 const int mt = s_tab->warp_tile[gw][slot];
-                if (mt < 0) break;
+                if (mt < 0 || LM_EXP == 1) break;
                 const int kb = s_tab->kb[mt], ndk = s_tab->ndk[mt];
                 const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 64 + lane;
                 // B operand: frame n = g of column block nb lives in warp row (8 nb + g) / FPW
@@ -646,11 +681,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             s_stat[tid] = st;
         }
 
+        LM_T(5);   // mel phase
         // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
         if (has1) {
             if (stage_gather(&s_ctx[ord1 & 1], tile1)) group_bar(group);   // (C) only for tiles that touch a clip edge
         }
 
+        LM_T(6);   // gather + barrier C
         // ---- per-clip normalisation --------------------------------------------------------------------
         if (tile + 1 == p.n_tiles) {
             if (p.normalize) {
@@ -694,7 +731,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         } else {
             ++tile;
         }
+        LM_T(7);   // normalisation
     }
+#if LM_TIMING
+    if (lane_ == 0) {
+        long long* o = g_timing + (static_cast<size_t>(blockIdx.x) * kWarps + (tid >> 5)) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = t_acc[i];
+    }
+#endif
 }
 
 }  // namespace lm

@@ -185,9 +185,12 @@ class LogMelPlan:
                      aug: Optional[np.ndarray] = None, noise: Optional[torch.Tensor] = None,
                      normalize: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host tensors in, host features out; H2D / kernel / D2H are pipelined inside the
-        library on plan-owned streams.  Pinned tensors make the copies asynchronous."""
+        library on plan-owned streams.  Pinned tensors make the copies asynchronous.
+        ``wave`` is fp32 samples or int16 PCM (decoded on the device as x / 32768: half the PCIe bytes)."""
         B = int(offset.numel())
-        for name, t, dt in (("wave", wave, torch.float32), ("offset", offset, torch.int64), ("length", length, torch.int32)):
+        if wave.dtype not in (torch.float32, torch.int16):
+            raise ValueError("wave must be fp32 samples or int16 PCM")
+        for name, t, dt in (("wave", wave, wave.dtype), ("offset", offset, torch.int64), ("length", length, torch.int32)):
             if t.device.type != "cpu" or t.dtype != dt or not t.is_contiguous():
                 raise ValueError(f"{name} must be a contiguous CPU {dt} tensor")
         if out is None:
@@ -203,7 +206,17 @@ class LogMelPlan:
         if noise is not None and (noise.device.type != "cpu" or noise.dtype != torch.float32
                                   or noise.numel() != B * self.target_length or not noise.is_contiguous()):
             raise ValueError("noise must be contiguous CPU fp32 [B, target_length]")
-        _lib.check(self._lib.lm_forward_host(self._h, wave.data_ptr(), int(wave.numel()), offset.data_ptr(),
-                                             length.data_ptr(), B, aug_ptr, _ptr(noise), out.data_ptr(),
-                                             1 if normalize else 0))
+        fn = self._lib.lm_forward_host_pcm16 if wave.dtype == torch.int16 else self._lib.lm_forward_host
+        _lib.check(fn(self._h, wave.data_ptr(), int(wave.numel()), offset.data_ptr(), length.data_ptr(), B, aug_ptr,
+                      _ptr(noise), out.data_ptr(), 1 if normalize else 0))
+        return out
+
+    def pcm16_decode(self, pcm: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device int16 PCM -> fp32 in [-1, 1) (x / 32768), what ``torchaudio.load`` returns for a 16-bit wav."""
+        if pcm.device != self.device or pcm.dtype != torch.int16 or not pcm.is_contiguous():
+            raise ValueError(f"pcm must be a contiguous int16 tensor on {self.device}")
+        if out is None:
+            out = torch.empty(pcm.shape, dtype=torch.float32, device=self.device)
+        s = torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.lm_pcm16_decode(pcm.data_ptr(), out.data_ptr(), int(pcm.numel()), C.c_void_p(s.cuda_stream)))
         return out

@@ -107,7 +107,7 @@ int lm_plan_info(const lm_plan* plan, lm_info* info);
 /* Tuning knobs for experiments: key "tma" (0/1), "max_ctas" (0 = SM count). */
 int lm_plan_set(lm_plan* plan, const char* key, int value);
 /* Number of kernels this plan has launched since creation (lm_forward: 1 per call,
- * lm_forward_host: 1 per chunk). */
+ * lm_forward_host: 1 per chunk, lm_forward_host_pcm16: 2 per chunk). */
 int64_t lm_plan_launch_count(const lm_plan* plan);
 
 /*
@@ -134,6 +134,22 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
 int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, const int64_t* offset,
                     const int32_t* length, int32_t B, const lm_aug* aug, const float* noise,
                     float* out, int32_t normalize);
+
+/*
+ * 16-bit PCM -> fp32 in [-1, 1): x / 32768, what torchaudio.load(normalize=True) hands the reference for a
+ * PCM_16 wav (R/src/data/preprocessing.py:57).  Device pointers, both 16-byte aligned.
+ */
+int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream);
+
+/*
+ * lm_forward_host for clips that are still 16-bit PCM (the sample format of the ICBHI wav files and of
+ * every temp wav the analyzers write): the int16 samples cross PCIe -- half the bytes of the fp32 call --
+ * and are decoded on the device (lm_pcm16_decode) in front of the log-mel kernel.  offset/length count
+ * samples.  Features are bit-identical to lm_forward_host on pcm[i] / 32768.
+ */
+int lm_forward_host_pcm16(lm_plan* plan, const int16_t* pcm, int64_t total_samples, const int64_t* offset,
+                          const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,
+                          int32_t normalize);
 
 /*
  * FlexibleAudioPreprocessor's tail for durations whose frame count differs from ceil(T/hop)

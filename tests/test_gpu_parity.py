@@ -293,3 +293,27 @@ def test_host_path_matches_device_path(A):
     out_d = plan.forward_dense(host.to(plan.device))
     torch.cuda.synchronize()
     assert torch.equal(out_h, out_d.cpu())
+
+
+def test_pcm16_host_path_matches_decoded_floats(A):
+    """lm_forward_host_pcm16 (int16 over PCIe, decoded on the device) == lm_forward on pcm / 32768, bit for
+    bit, for ragged clips that start at odd sample offsets; lm_pcm16_decode itself is exact."""
+    plan = get_plan(A)
+    rs = np.random.RandomState(5)
+    lens = [80000, 12345, 80001, 0, 99999, 80000, 7, 64000]
+    starts, pos = [], 3
+    for n in lens:
+        starts.append(pos)
+        pos += n + 5
+    pcm = torch.from_numpy(rs.randint(-32768, 32768, size=pos).astype(np.int16)).pin_memory()
+    offset = torch.tensor(starts, dtype=torch.int64)
+    length = torch.tensor(lens, dtype=torch.int32)
+    out_h = plan.forward_host(pcm, offset, length)
+    dec = plan.pcm16_decode(pcm.to(plan.device))
+    assert torch.equal(dec.cpu(), pcm.float() / 32768.0)
+    out_d = plan.forward(dec, offset.to(plan.device), length.to(plan.device))
+    torch.cuda.synchronize()
+    assert torch.equal(out_h, out_d.cpu())
+    # against the oracle on the decoded floats
+    ref = O.logmel((pcm[starts[0]:starts[0] + lens[0]].float() / 32768.0).numpy(), O.OracleConfig())
+    assert np.abs(out_h[0, 0].numpy() - ref).max() < NORM_ATOL
