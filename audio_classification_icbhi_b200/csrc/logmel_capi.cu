@@ -263,7 +263,7 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     std::vector<float2> tw(32 * lm::kTwRows), utw(512);
     const double two_pi = 6.283185307179586476925286766559;
     for (int r = 0; r < lm::kTwRows; ++r) {
-        const int k1 = r < 3 ? r + 1 : 4 * (r - 2);   // 1, 2, 3, 4, 8, ..., 28
+        const int k1 = (lm::kTwRows == 31) ? r + 1 : (r < 3 ? r + 1 : 4 * (r - 2));   // 1..31, or 1, 2, 3, 4, 8, ..., 28
         for (int n2 = 0; n2 < 32; ++n2) {
             const double a = two_pi * static_cast<double>(k1 * n2) / 1024.0;
             tw[r * 32 + n2] = make_float2(static_cast<float>(cos(a)), static_cast<float>(-sin(a)));

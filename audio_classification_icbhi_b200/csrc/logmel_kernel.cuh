@@ -53,6 +53,9 @@
 #ifndef LM_TIMING
 #define LM_TIMING 0
 #endif
+#ifndef LM_TW2
+#define LM_TW2 1   // 1: twiddle = product of two table entries (10 table rows); 0: full table (31 rows, 8 KB)
+#endif
 #if LM_TIMING
 #define LM_T(slot) do { const long long t_now_ = clock64(); t_acc[slot] += t_now_ - t_last; t_last = t_now_; } while (0)
 #else
@@ -208,8 +211,20 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 //           separately; the LDS.128 reads hand the second FFT register pairs of neighbouring
 //           points, the layout its packed stages 1-4 want -- see gen_fft.py) + second radix-32 FFT.
 // ---------------------------------------------------------------------------------------
+#if LM_TW2
 constexpr int kTwRows = 10;   // twiddle table rows kept on chip: k1 = 1, 2, 3, 4, 8, 12, ..., 28
+#else
+constexpr int kTwRows = 31;   // k1 = 1 .. 31
+#endif
 __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
+#if !LM_TW2
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) {
+        const float2 w = tw[(k1 - 1) * 32 + lane];   // (cos, -sin): (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy)
+        z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-w.y, w.y), lm_mul2(z[k1], lm_bcast(w.x)));
+    }
+    return;
+#endif
     // Twiddle W1024^(lane*k1), k1 = 4a + b, as the product of two table entries W^(4a*lane) * W^(b*lane):
     // 10 shared-memory loads instead of 31 (the shared-memory pipe is the tighter resource here, and
     // 31 loads in flight on top of z do not fit the register file), one extra rounding per twiddle.
