@@ -14,6 +14,7 @@ from .analyzer import SlidingWindowLogMel, segment_offsets
 from .segmenter import ICBHISegmenter
 from .sharding import ShardedLogMel, shard_bounds, shard_size
 from .augment import draw_fast_augmentation, draw_reference_augmentation
+from .resample import Resampler, get_resampler
 
 __all__ = [
     "LogMelPlan", "make_aug_array", "reference_filterbank", "reference_window",
@@ -22,5 +23,6 @@ __all__ = [
     "SlidingWindowLogMel", "segment_offsets", "ICBHISegmenter",
     "ShardedLogMel", "shard_bounds", "shard_size",
     "draw_fast_augmentation", "draw_reference_augmentation",
+    "Resampler", "get_resampler",
 ]
 __version__ = "0.1.0"

@@ -112,4 +112,29 @@ __global__ void pcm16_decode_kernel(const int16_t* __restrict__ in, float* __res
     for (long long i = (n8 << 3) + tid; i < n; i += stride) out[i] = static_cast<float>(in[i]) * k;
 }
 
+// Polyphase sinc resampler = torchaudio.transforms.Resample(orig, new) with its defaults, the resampler of
+// AudioPreprocessor.load_audio (R/src/data/preprocessing.py:63-65; TA/functional/functional.py
+// _get_sinc_resample_kernel / _apply_sinc_resample_kernel).  With o = orig/gcd, q = new/gcd and
+// xpad = pad(x, (width, width + o)):   y[m q + p] = sum_k kernel[p][k] xpad[m o + k],  k < 2 width + o.
+// torchaudio runs that as a dense conv1d; all but ~2 width + 1 taps of a phase are (numerically) zero, so
+// the host keeps, per phase, the window of `ntaps` taps around the phase's centre and the kernel walks only
+// those.  One output sample per thread; a block's outputs share their input span through L1.
+__global__ void resample_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out,
+                                const float* __restrict__ taps, const int* __restrict__ k0, int o, int q, int ntaps,
+                                int width) {
+    const long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const long long m = j / q;
+    const int p = static_cast<int>(j - m * q);
+    const float* __restrict__ w = taps + static_cast<size_t>(p) * ntaps;
+    const long long base = m * o + k0[p] - width;   // index into x of tap 0
+    float acc = 0.0f;
+    for (int i = 0; i < ntaps; ++i) {
+        const long long xi = base + i;
+        const float v = (xi >= 0 && xi < n_in) ? __ldg(x + xi) : 0.0f;
+        acc = fmaf(w[i], v, acc);
+    }
+    y[j] = acc;
+}
+
 }  // namespace lm

@@ -388,6 +388,103 @@ int lm_pcm16_roundtrip(const float* in, float* out, int64_t n, void* cuda_stream
     return LM_OK;
 }
 
+// ---- polyphase sinc resampler (torchaudio.transforms.Resample defaults) ---------------------------------------
+struct lm_resampler {
+    int device = 0, orig = 1, neu = 1;   // after division by the gcd
+    int width = 0, ntaps = 0;
+    float* d_taps = nullptr;
+    int* d_k0 = nullptr;
+};
+
+int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resampler** out) {
+    if (!out || orig_freq < 1 || new_freq < 1) return LM_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return LM_ERR_NO_DEVICE;
+    }
+    LM_CUDA(cudaSetDevice(device));
+    int a = orig_freq, b = new_freq;
+    while (b) { const int t = a % b; a = b; b = t; }
+    const int o = orig_freq / a, q = new_freq / a;
+    // TA/functional/functional.py _get_sinc_resample_kernel with lowpass_filter_width = 6, rolloff = 0.99,
+    // sinc_interp_hann, float64 index arithmetic, kernel rounded to float32 at the end
+    const int lpw = 6;
+    const double base_freq = std::min(o, q) * 0.99;
+    const int width = static_cast<int>(ceil(lpw * o / base_freq));
+    const int K = 2 * width + o;
+    const double pi = 3.14159265358979323846;
+    std::vector<float> dense(static_cast<size_t>(q) * K);
+    for (int p = 0; p < q; ++p)
+        for (int k = 0; k < K; ++k) {
+            double t = (static_cast<double>(-p) / q + static_cast<double>(k - width) / o) * base_freq;
+            t = std::min(std::max(t, -static_cast<double>(lpw)), static_cast<double>(lpw));
+            const double c = cos(t * pi / lpw / 2.0);
+            const double window = c * c;
+            const double tp = t * pi;
+            const double sinc = (tp == 0.0) ? 1.0 : sin(tp) / tp;
+            dense[static_cast<size_t>(p) * K + k] = static_cast<float>(sinc * window * (base_freq / o));
+        }
+    // per phase keep the taps that are not negligible (|w| > 1e-12: the clamped tails are ~1e-33)
+    int ntaps = 1;
+    std::vector<int> k0(q), k1(q);
+    for (int p = 0; p < q; ++p) {
+        int lo = K, hi = -1;
+        for (int k = 0; k < K; ++k)
+            if (fabsf(dense[static_cast<size_t>(p) * K + k]) > 1e-12f) { lo = std::min(lo, k); hi = k; }
+        if (hi < 0) { lo = 0; hi = 0; }
+        k0[p] = lo; k1[p] = hi;
+        ntaps = std::max(ntaps, hi - lo + 1);
+    }
+    std::vector<float> taps(static_cast<size_t>(q) * ntaps, 0.0f);
+    for (int p = 0; p < q; ++p) {
+        if (k0[p] + ntaps > K) k0[p] = std::max(0, K - ntaps);
+        for (int i = 0; i < ntaps && k0[p] + i < K; ++i) taps[static_cast<size_t>(p) * ntaps + i] = dense[static_cast<size_t>(p) * K + k0[p] + i];
+    }
+    lm_resampler* r = new (std::nothrow) lm_resampler();
+    if (!r) return LM_ERR_INVALID_ARG;
+    r->device = device; r->orig = o; r->neu = q; r->width = width; r->ntaps = ntaps;
+    if (cudaMalloc(&r->d_taps, sizeof(float) * taps.size()) != cudaSuccess ||
+        cudaMalloc(&r->d_k0, sizeof(int) * q) != cudaSuccess ||
+        cudaMemcpy(r->d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(r->d_k0, k0.data(), sizeof(int) * q, cudaMemcpyHostToDevice) != cudaSuccess) {
+        const int rc = cuda_fail(cudaGetLastError(), "resampler tables");
+        cudaFree(r->d_taps); cudaFree(r->d_k0);
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return LM_OK;
+}
+
+int lm_resampler_destroy(lm_resampler* r) {
+    if (!r) return LM_OK;
+    cudaSetDevice(r->device);
+    cudaFree(r->d_taps); cudaFree(r->d_k0);
+    delete r;
+    return LM_OK;
+}
+
+int64_t lm_resampler_out_len(const lm_resampler* r, int64_t in_len) {
+    if (!r || in_len < 0) return LM_ERR_INVALID_ARG;
+    return (static_cast<int64_t>(r->neu) * in_len + r->orig - 1) / r->orig;   // ceil(new * len / orig)
+}
+
+int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* out, void* cuda_stream) {
+    if (!r || in_len < 0) return LM_ERR_INVALID_ARG;
+    const int64_t n_out = lm_resampler_out_len(r, in_len);
+    if (n_out == 0) return LM_OK;
+    if (!in || !out) return LM_ERR_INVALID_ARG;
+    const int threads = 256;
+    const long long blocks = (n_out + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return LM_ERR_INVALID_ARG;
+    lm::resample_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        in, in_len, out, n_out, r->d_taps, r->d_k0, r->orig, r->neu, r->ntaps, r->width);
+    LM_CUDA(cudaGetLastError());
+    return LM_OK;
+}
+
 int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream) {
     if (n < 0) return LM_ERR_INVALID_ARG;
     if (n == 0) return LM_OK;

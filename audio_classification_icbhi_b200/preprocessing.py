@@ -87,8 +87,9 @@ class AudioPreprocessor:
         if waveform.shape[0] > 1:
             waveform = torch.mean(waveform, dim=0, keepdim=True)
         if sr != self.sample_rate:
-            import torchaudio.transforms as T   # sinc resampler the reference uses (host side)
-            waveform = T.Resample(sr, self.sample_rate)(waveform)
+            # T.Resample(sr, self.sample_rate) of the reference (preprocessing.py:63-65), as a CUDA kernel
+            from .resample import get_resampler
+            waveform = get_resampler(int(sr), int(self.sample_rate), self.plan.device)(waveform.float()).cpu()
         return waveform
 
     def pad_or_crop(self, waveform):

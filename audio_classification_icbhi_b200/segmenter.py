@@ -4,8 +4,8 @@ ICBHI recordings into per-cycle clips, class directories and a stats JSON.
 This is file plumbing around the hot path (SURVEY.md section 8f "next"): decode, slice by
 annotation row, drop cycles shorter than `min_duration`, write PCM_16 wavs.  Decoding uses the
 stdlib reader in wavio.py (librosa / soundfile are not in the image); recordings whose rate
-differs from `sample_rate` are resampled with torchaudio's sinc resampler on the host -- librosa's
-soxr resampler is a different filter, so resampled segments are "parity unpinned".
+differs from `sample_rate` are resampled with the library's CUDA port of torchaudio's sinc resampler
+(resample.py) -- librosa's soxr resampler is a different filter, so resampled segments are "parity unpinned".
 `segments_to_features` is the new bit: the cycles of a recording go to the GPU as (offset, length)
 pairs into the one uploaded recording, with no intermediate files.
 """
@@ -74,8 +74,8 @@ class ICBHISegmenter:
         data, sr = read_wav(str(audio_path))
         mono = data.mean(axis=0) if data.shape[0] > 1 else data[0]
         if sr != self.sample_rate:
-            import torchaudio.transforms as T
-            mono = T.Resample(sr, self.sample_rate)(torch.from_numpy(mono).unsqueeze(0))[0].numpy()
+            from .resample import get_resampler
+            mono = get_resampler(int(sr), int(self.sample_rate))(torch.from_numpy(np.ascontiguousarray(mono, dtype=np.float32))).cpu().numpy()
         return np.ascontiguousarray(mono, dtype=np.float32)
 
     def cycle_table(self, n_samples: int, annotations) -> List[Tuple[int, int, int, str]]:

@@ -136,6 +136,20 @@ int lm_forward_host(lm_plan* plan, const float* wave, int64_t total_samples, con
                     float* out, int32_t normalize);
 
 /*
+ * Polyphase sinc resampler on the device = torchaudio.transforms.Resample(orig_freq, new_freq) with its
+ * defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99), the resampler of
+ * AudioPreprocessor.load_audio (R/src/data/preprocessing.py:63-65): ICBHI ships 4, 10 and 44.1 kHz
+ * recordings.  Mono; `in` / `out` are device pointers; out holds lm_resampler_out_len(r, in_len) =
+ * ceil(new_freq * in_len / orig_freq) samples.  Float arithmetic: agrees with torchaudio to ~1e-6 of
+ * full scale (torchaudio sums the same products as a dense conv1d, in another order).
+ */
+typedef struct lm_resampler lm_resampler;
+int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resampler** r);
+int lm_resampler_destroy(lm_resampler* r);
+int64_t lm_resampler_out_len(const lm_resampler* r, int64_t in_len);
+int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* out, void* cuda_stream);
+
+/*
  * 16-bit PCM -> fp32 in [-1, 1): x / 32768, what torchaudio.load(normalize=True) hands the reference for a
  * PCM_16 wav (R/src/data/preprocessing.py:57).  Device pointers, both 16-byte aligned.
  */

@@ -401,3 +401,42 @@ def replay_augmentation(np_rs: np.random.RandomState, torch_gen: TorchCpuGenerat
         t0, t1 = _mask_interval(torch_gen, time_mask_param, frames)
         out.append(AugDraw(noise, shift, f0, f1, t0, t1, noise_values))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Resampling step of load_audio (R/src/data/preprocessing.py:63-65: T.Resample(sr, sample_rate))
+# ----------------------------------------------------------------------------------------------
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """TA/functional/functional.py `_get_sinc_resample_kernel` (sinc_interp_hann), float64 throughout.
+    Returns (kernel [new/gcd, 2*width + orig/gcd], width, orig/gcd, new/gcd)."""
+    g = int(np.gcd(int(orig_freq), int(new_freq)))
+    o, q = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(o, q) * rolloff
+    width = int(np.ceil(lowpass_filter_width * o / base_freq))
+    idx = np.arange(-width, width + o, dtype=np.float64)[None, :] / o
+    t = np.arange(0, -q, -1, dtype=np.float64)[:, None] / q + idx
+    t = np.clip(t * base_freq, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * np.pi / lowpass_filter_width / 2.0) ** 2
+    t = t * np.pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sinc = np.where(t == 0.0, 1.0, np.sin(t) / t)
+    return sinc * window * (base_freq / o), width, o, q
+
+
+def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """TA/functional/functional.py `_apply_sinc_resample_kernel` on a 1-D waveform: zero-pad by (width,
+    width + orig), correlate with each of the `new` phase kernels at stride `orig`, interleave the phases,
+    keep ceil(new * len / orig) samples.  float64 (the reference accumulates in float32)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    if int(orig_freq) == int(new_freq):
+        return x.copy()
+    kernel, width, o, q = sinc_resample_kernel(orig_freq, new_freq)
+    n = x.shape[0]
+    xp = np.concatenate([np.zeros(width), x, np.zeros(width + o)])
+    K = kernel.shape[1]
+    n_blocks = (xp.shape[0] - K) // o + 1
+    starts = np.arange(n_blocks) * o
+    windows = np.lib.stride_tricks.sliding_window_view(xp, K)[starts]     # [blocks, K]
+    y = (windows @ kernel.T).reshape(-1)                                  # block-major, phase-minor
+    target = int(np.ceil(q * n / o))
+    return y[:target]

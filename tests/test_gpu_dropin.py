@@ -196,3 +196,37 @@ def test_unsupported_configurations_fail_loudly():
             A.AudioPreprocessor(**kw).plan
     with pytest.raises(RuntimeError, match="target_len must exceed"):
         A.AudioPreprocessor(duration=0.05).plan
+
+
+@pytest.mark.parametrize("sr", [4000, 10000, 44100, 8000, 22050, 48000])
+def test_gpu_resampler_matches_torchaudio_golden_and_oracle(sr):
+    """lm_resample (CUDA polyphase sinc) against T.Resample(sr, 16000) as the reference calls it
+    (golden, generated from torchaudio) and against the float64 oracle: 1e-5 / 2e-6 of full scale."""
+    import os
+    from oracle import logmel_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample_golden.npz"))
+    x = g[f"in/{sr}"]
+    r = A.get_resampler(sr, 16000)
+    y = r(torch.from_numpy(x)).cpu().numpy()
+    assert y.shape == g[f"out/{sr}"].shape and r.out_len(len(x)) == len(y)
+    assert np.abs(y - g[f"out/{sr}"]).max() < 1e-5
+    assert np.abs(y - O.resample(x, sr, 16000)).max() < 2e-6
+    y2 = r(torch.from_numpy(np.stack([x, 0.5 * x]))).cpu().numpy()      # [channels, len]
+    np.testing.assert_array_equal(y2[0], y)
+    assert r(torch.zeros(0)).numel() == 0
+
+
+def test_load_audio_resamples_on_the_gpu(tmp_path):
+    """load_audio of a 4 kHz PCM16 wav -> 16 kHz mono through the CUDA resampler (preprocessing.py:55-68)."""
+    from oracle import logmel_oracle as O
+    rs = np.random.RandomState(3)
+    x = (rs.standard_normal(4000) * 0.2).clip(-1, 1)
+    path = str(tmp_path / "lo.wav")
+    wavio.write_wav_pcm16(path, x, 4000)
+    p = A.AudioPreprocessor()
+    w = p.load_audio(path)
+    assert w.shape == (1, 16000) and w.dtype == torch.float32 and w.device.type == "cpu"
+    q = np.rint(x * 32767) / 32768.0
+    assert np.abs(w[0].numpy() - O.resample(q, 4000, 16000)).max() < 2e-6
+    feats = p.preprocess(path)
+    assert feats.shape == (1, 128, 157)

@@ -1,6 +1,8 @@
 """Pins the numpy oracle (oracle/logmel_oracle.py) against outputs of the reference classes
 (tests/golden/reference_golden.npz, produced by tests/golden/make_golden.py in the build
 container).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -131,3 +133,16 @@ def test_segment_offsets_known_answers():
     assert len(O.segment_offsets(3600 * 16000, 16000, 5.0, 0.5)) == 1440
     assert O.segment_offsets(100, 16000, 1.0, 0.5) == [(0, 100, 0.0, 100 / 16000)]
     assert O.segment_offsets(0, 16000, 1.0, 0.5) == []
+
+
+@pytest.mark.parametrize("sr", [4000, 10000, 44100, 8000, 22050, 48000])
+def test_oracle_resample_matches_torchaudio_golden(sr):
+    """oracle.resample (float64) against T.Resample(sr, 16000) run by tests/golden/make_resample_golden.py --
+    the reference's own call (R/src/data/preprocessing.py:63-65).  The reference sums up to 475 float32
+    products per sample: its own distance to float64 is ~3e-6."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resample_golden.npz"))
+    y = O.resample(g[f"in/{sr}"], sr, 16000)
+    assert y.shape == g[f"out/{sr}"].shape
+    assert np.abs(y - g[f"out/{sr}"]).max() < 1e-5
+    k, width, o, q = O.sinc_resample_kernel(sr, 16000)
+    assert k.shape == (q, 2 * width + o)
