@@ -12,7 +12,7 @@ from .preprocessing_flexible import FlexibleAudioPreprocessor
 from .dataset import GpuCollate, ICBHIDataset, ICBHISegmentedDataset
 from .analyzer import SlidingWindowLogMel, segment_offsets
 from .segmenter import ICBHISegmenter
-from .sharding import ShardedLogMel, shard_bounds, shard_size
+from .sharding import FusedGather, ShardedLogMel, shard_bounds, shard_size
 from .augment import draw_fast_augmentation, draw_reference_augmentation
 from .resample import Resampler, get_resampler
 
@@ -21,7 +21,7 @@ __all__ = [
     "AudioPreprocessor", "FlexibleAudioPreprocessor",
     "ICBHIDataset", "ICBHISegmentedDataset", "GpuCollate",
     "SlidingWindowLogMel", "segment_offsets", "ICBHISegmenter",
-    "ShardedLogMel", "shard_bounds", "shard_size",
+    "ShardedLogMel", "FusedGather", "shard_bounds", "shard_size",
     "draw_fast_augmentation", "draw_reference_augmentation",
     "Resampler", "get_resampler",
 ]

@@ -61,6 +61,8 @@ EXPORTS = {
     "lm_pcm16_roundtrip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lm_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "lm_forward_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "lm_pcm16_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "lm_resampler_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
     "lm_resampler_destroy": (C.c_int, [C.c_void_p]),

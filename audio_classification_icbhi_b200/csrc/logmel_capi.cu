@@ -94,9 +94,12 @@ lm::KParams make_params(const lm_plan* p) {
 
 int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
            const lm_aug* aug, const float* noise, float* out_norm, float* out_db, float* out_melpow,
-           int32_t normalize, cudaStream_t stream) {
+           int32_t normalize, cudaStream_t stream, float* const* peers = nullptr, int n_peers = 0,
+           float* mc_out = nullptr) {
     if (B == 0) return LM_OK;
     lm::KParams k = make_params(p);
+    for (int r = 0; r < n_peers; ++r) k.peer[r] = peers[r];
+    k.n_peer = n_peers; k.mc_out = mc_out;
     k.wave = wave; k.offset = reinterpret_cast<const long long*>(offset); k.length = length;
     k.aug = aug; k.noise = noise; k.out_norm = out_norm; k.out_db = out_db; k.out_melpow = out_melpow;
     k.B = B; k.normalize = normalize;
@@ -363,6 +366,26 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
     if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
     const int rc = launch(plan, wave, offset, length, B, aug, noise, out_norm, out_db, out_melpow, normalize,
                           static_cast<cudaStream_t>(cuda_stream));
+    if (dev != plan->device) cudaSetDevice(dev);
+    return rc;
+}
+
+int lm_forward_gather(lm_plan* plan, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
+                      const lm_aug* aug, const float* noise, float* out_slice, float* const* peer_slices,
+                      int32_t n_peers, float* mc_slice, void* cuda_stream) {
+    if (!plan || B < 0 || n_peers < 0 || n_peers > lm::kMaxPeers) return LM_ERR_INVALID_ARG;
+    if (B == 0) return LM_OK;
+    if (!wave || !offset || !length || !out_slice || (n_peers > 0 && !peer_slices)) return LM_ERR_INVALID_ARG;
+    // the gather rides on the 16-byte stores of the normalisation pass
+    if ((static_cast<size_t>(plan->n_mels) * plan->frames) % 4 != 0) return LM_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(out_slice) & 15u) || (reinterpret_cast<uintptr_t>(mc_slice) & 15u)) return LM_ERR_INVALID_ARG;
+    for (int r = 0; r < n_peers; ++r)
+        if (!peer_slices[r] || (reinterpret_cast<uintptr_t>(peer_slices[r]) & 15u)) return LM_ERR_INVALID_ARG;
+    int dev = -1;
+    LM_CUDA(cudaGetDevice(&dev));
+    if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
+    const int rc = launch(plan, wave, offset, length, B, aug, noise, out_slice, nullptr, nullptr, 1,
+                          static_cast<cudaStream_t>(cuda_stream), peer_slices, n_peers, mc_slice);
     if (dev != plan->device) cudaSetDevice(dev);
     return rc;
 }

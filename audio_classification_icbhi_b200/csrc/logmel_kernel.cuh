@@ -77,6 +77,7 @@ constexpr int kScrPitch = 36;                 // transpose rows: 32 + 4 (16 B al
 constexpr int kRowFloats = 1168;              // per-warp row: >= 32*36 and == 16 (mod 32) for the MMA loads
 constexpr int kPbOff = 528;                   // n_fft=1024: second frame's spectrum inside the row (== 16 mod 32)
 constexpr int kMaxMelTiles = 32;              // n_mels <= 256
+constexpr int kMaxPeers = 7;                  // other GPUs of one NVSwitch domain
 constexpr int kTileSlots = kMaxMelTiles / kGroupWarps;   // mel tiles per warp, at most
 constexpr int kMaxDk = 96;                    // 16-bin steps of banded filterbank kept on chip (1 KB each)
 
@@ -99,6 +100,13 @@ struct KParams {
     float* __restrict__ out_melpow;
     int B;
     int normalize;
+    // fused feature all-gather (lm_forward_gather): besides out_norm, the normalised features of clip i go to
+    // peer[r] + i * n_mels * frames for r < n_peer (the same slice of the other ranks' gathered buffers,
+    // mapped over NVLink), or through one multicast store per value when mc_out is set (NVSwitch replicates
+    // it into every rank's buffer, this rank's included)
+    float* peer[kMaxPeers];
+    int n_peer;
+    float* mc_out;
     // plan
     int T, hop, frames, n_mels, n_tiles;
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
@@ -169,6 +177,12 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ int launder(int v) {
     asm volatile("" : "+r"(v));
     return v;
+}
+// one 16-byte store replicated by the NVSwitch into every GPU of the multicast group
+__device__ __forceinline__ void multimem_st_v4(float* mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 // log2 of a normal positive number: plain MUFU.LG2, no denormal pre-scaling (callers pass x > amin)
 __device__ __forceinline__ float lg2_ftz(float x) {
@@ -729,13 +743,31 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 const float mean = bcast[0], inv = 1.0f / bcast[1];
                 float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
                 const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
-                for (int i = gtid; i < n4; i += kGroupThreads) {
-                    float4 v = __ldcg(o4 + i);
-                    v.x = (v.x - mean) * inv;
-                    v.y = (v.y - mean) * inv;
-                    v.z = (v.z - mean) * inv;
-                    v.w = (v.w - mean) * inv;
-                    o4[i] = v;
+                if (p.mc_out == nullptr && p.n_peer == 0) {
+                    for (int i = gtid; i < n4; i += kGroupThreads) {
+                        float4 v = __ldcg(o4 + i);
+                        v.x = (v.x - mean) * inv;
+                        v.y = (v.y - mean) * inv;
+                        v.z = (v.z - mean) * inv;
+                        v.w = (v.w - mean) * inv;
+                        o4[i] = v;
+                    }
+                } else {
+                    // fused all-gather: the same 16 bytes also go to the other ranks' buffers
+                    const size_t gofs = static_cast<size_t>(clip) * clip_elems;   // the clip's offset inside a rank's slice
+                    for (int i = gtid; i < n4; i += kGroupThreads) {
+                        float4 v = __ldcg(o4 + i);
+                        v.x = (v.x - mean) * inv;
+                        v.y = (v.y - mean) * inv;
+                        v.z = (v.z - mean) * inv;
+                        v.w = (v.w - mean) * inv;
+                        if (p.mc_out != nullptr) {
+                            multimem_st_v4(p.mc_out + gofs + 4 * static_cast<size_t>(i), v);   // lands here and on every peer
+                        } else {
+                            o4[i] = v;
+                            for (int r = 0; r < p.n_peer; ++r) reinterpret_cast<float4*>(p.peer[r] + gofs)[i] = v;
+                        }
+                    }
                 }
                 for (int i = (n4 << 2) + gtid; i < static_cast<int>(clip_elems); i += kGroupThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;

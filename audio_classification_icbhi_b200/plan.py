@@ -158,6 +158,25 @@ class LogMelPlan:
                                         1 if normalize else 0, C.c_void_p(s.cuda_stream)))
         return out
 
+    def forward_gather(self, wave: torch.Tensor, offset: torch.Tensor, length: torch.Tensor, out_slice_ptr: int,
+                       peer_slice_ptrs=(), mc_slice_ptr: int = 0, aug: Optional[torch.Tensor] = None,
+                       noise: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """`forward` fused with the feature all-gather: the normalised features also go to the same slice of
+        the other ranks' gathered buffers (`peer_slice_ptrs`: device addresses mapped into this process, e.g.
+        `torch.distributed._symmetric_memory` buffer pointers + slice offset) or through the multicast address
+        `mc_slice_ptr`.  See `sharding.FusedGather`."""
+        B = int(offset.numel())
+        for name, t, dt in (("wave", wave, torch.float32), ("offset", offset, torch.int64), ("length", length, torch.int32)):
+            if t.device != self.device or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
+        peers = [int(x) for x in peer_slice_ptrs]
+        arr = (C.c_void_p * max(len(peers), 1))(*peers) if peers else None
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        _lib.check(self._lib.lm_forward_gather(self._h, wave.data_ptr(), offset.data_ptr(), length.data_ptr(), B,
+                                               _ptr(aug), _ptr(noise), C.c_void_p(int(out_slice_ptr)), arr, len(peers),
+                                               C.c_void_p(int(mc_slice_ptr)) if mc_slice_ptr else None,
+                                               C.c_void_p(s.cuda_stream)))
+
     @property
     def launches(self) -> int:
         """Kernels launched through this plan so far (counted inside the library)."""

@@ -14,7 +14,7 @@ from typing import Callable, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_size", "ShardedLogMel"]
+__all__ = ["shard_bounds", "shard_size", "ShardedLogMel", "FusedGather"]
 
 
 def shard_size(n_items: int, world: int) -> int:
@@ -64,3 +64,50 @@ class ShardedLogMel:
         else:
             full.copy_(block)
         return full[:n]
+
+
+class FusedGather:
+    """Feature all-gather fused into the log-mel kernel (`lm_forward_gather`).
+
+    Every rank allocates the gathered buffer `[world * per_rank, 1, n_mels, frames]` in symmetric memory
+    (`torch.distributed._symmetric_memory`: the same allocation on every GPU of the NVSwitch domain, mapped
+    into every process).  `run` launches the kernel once; its clip-end normalisation pass stores this
+    rank's features into its slice of EVERY rank's buffer -- one `multimem.st` per 16 bytes when the group
+    has a multicast address (the switch replicates it), plain stores to the peers' mapped buffers
+    otherwise -- so the transfer overlaps the compute of the remaining clips.  `finish` is the rank
+    barrier after which `self.full` holds all ranks' features.  NCCL (`ShardedLogMel.gathered`) remains
+    the path for ranks without peer access."""
+
+    def __init__(self, plan, per_rank: int, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        self.plan = plan
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world - 1 > 7:
+            raise ValueError("lm_forward_gather addresses at most 7 peers")
+        self.per_rank = int(per_rank)
+        self.clip_elems = plan.n_mels * plan.frames
+        n = self.world * self.per_rank * self.clip_elems
+        self._flat = symm.empty(n, dtype=torch.float32, device=plan.device)
+        self._hdl = symm.rendezvous(self._flat, self.group)
+        self.full = self._flat.view(self.world * self.per_rank, 1, plan.n_mels, plan.frames)
+        off = self.rank * self.per_rank * self.clip_elems * 4
+        ptrs = [int(x) for x in self._hdl.buffer_ptrs]
+        self.out_slice_ptr = ptrs[self.rank] + off
+        self.peer_slice_ptrs = [ptrs[r] + off for r in range(self.world) if r != self.rank]
+        mc = int(self._hdl.multicast_ptr) if (use_multicast and self._hdl.has_multicast_support) else 0
+        self.mc_slice_ptr = mc + off if mc else 0
+
+    @property
+    def mode(self) -> str:
+        return "multimem.st (NVSwitch multicast)" if self.mc_slice_ptr else "st.global to peer-mapped buffers"
+
+    def run(self, wave: torch.Tensor, offset: torch.Tensor, length: torch.Tensor, **kw) -> None:
+        if int(offset.numel()) > self.per_rank:
+            raise ValueError("more clips than the rank's slice holds")
+        self.plan.forward_gather(wave, offset, length, self.out_slice_ptr, self.peer_slice_ptrs, self.mc_slice_ptr, **kw)
+
+    def finish(self) -> torch.Tensor:
+        """Rank barrier on the current stream (symmetric-memory signal pads): afterwards every slice is complete."""
+        self._hdl.barrier()
+        return self.full

@@ -303,6 +303,30 @@ def run_b200(args) -> None:
         gathered = {"value": world * BATCH * g_steps / (float(g_ms.item()) * 1e-3), "unit": UNIT,
                     "collective": "nccl all_gather_into_tensor", "bytes_per_rank": int(out.numel() * 4)}
 
+    # ---- the same gather fused into the kernel: stores to peer / multicast memory from the epilogue ----------
+    if world > 1 and gathered is not None:
+        try:
+            from audio_classification_icbhi_b200 import FusedGather
+            fg = FusedGather(plan, BATCH)
+            for _ in range(2):
+                fg.run(wave, offset, length)
+                fg.finish()
+            barrier()
+            f_ok = bool(torch.equal(fg.full, full))
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(g_steps):
+                fg.run(wave, offset, length)
+                fg.finish()
+            f1.record()
+            torch.cuda.synchronize()
+            f_ms = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(f_ms, op=dist.ReduceOp.MAX)
+            gathered["fused"] = {"value": world * BATCH * g_steps / (float(f_ms.item()) * 1e-3), "unit": UNIT,
+                                 "collective": "lm_forward_gather: " + fg.mode, "matches_nccl_gather": f_ok}
+        except Exception as e:   # no peer access / symmetric memory on this box: NCCL figure stands alone
+            gathered["fused"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     sampler.stop()
     sampler.join(timeout=1.0)
     clocks = sampler.summary()

@@ -125,6 +125,24 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
                float* out_melpow, int32_t normalize, void* cuda_stream);
 
 /*
+ * lm_forward fused with the feature all-gather of the multi-GPU layout (the reference
+ * has no multi-GPU path -- its consumer, R/src/training/trainer_fixed.py, is single-device).  Every rank owns
+ * the same slice [rank*B, rank*B + B) of a gathered buffer [world*B, 1, n_mels, frames] that exists on every
+ * GPU.  The kernel writes this rank's normalised features to
+ *   out_slice              its slice of its OWN gathered buffer, and
+ *   peer_slices[r], r < n_peers (<= 7)   the same slice of the OTHER ranks' buffers, mapped into this process
+ *                          (CUDA IPC / symmetric memory) and reached over NVLink by plain 16-byte stores, or
+ *   mc_slice (optional)    the slice's multicast address: ONE multimem.st per 16 bytes, replicated by the
+ *                          NVSwitch into every rank's buffer (then peer_slices is ignored and may be NULL).
+ * The stores ride on the clip-end normalisation pass, so the transfer overlaps the remaining clips' compute.
+ * The caller synchronises the ranks (a barrier after the stream has drained) before reading foreign slices.
+ * Needs n_mels*frames % 4 == 0 and 16-byte aligned slices.
+ */
+int lm_forward_gather(lm_plan* plan, const float* wave, const int64_t* offset, const int32_t* length,
+                      int32_t B, const lm_aug* aug, const float* noise, float* out_slice,
+                      float* const* peer_slices, int32_t n_peers, float* mc_slice, void* cuda_stream);
+
+/*
  * Host-buffer forward: the call a reference user makes.  All pointers are HOST pointers
  * (pinned memory makes the copies asynchronous).  Clips are cut into chunks; the H2D copy of
  * chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap on plan-owned
