@@ -317,3 +317,38 @@ def test_pcm16_host_path_matches_decoded_floats(A):
     # against the oracle on the decoded floats
     ref = O.logmel((pcm[starts[0]:starts[0] + lens[0]].float() / 32768.0).numpy(), O.OracleConfig())
     assert np.abs(out_h[0, 0].numpy() - ref).max() < NORM_ATOL
+
+
+def test_icbhi_sized_ragged_corpus(A):
+    """BASELINE configs[2] at full size on one GPU: ~6900 respiratory cycles of lognormal length
+    (0.2 .. 16.2 s), packed back to back, pad / centre-crop to 5 s.  Properties that do not
+    depend on the size (per-clip mean 0 / std 1, frame count, exact -100 dB floor in the padding of short
+    clips) plus spot clips -- the shortest, the longest, a cropped and a padded one -- against the oracle."""
+    plan = get_plan(A)
+    dev = plan.device
+    n, T = 6900, 80000
+    rs = np.random.RandomState(0)
+    secs = np.clip(rs.lognormal(np.log(2.5), 0.5, n), 0.2, 16.2)
+    lens = (secs * 16000).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum((lens + 3) // 4 * 4)[:-1]])
+    g = torch.Generator(device=dev).manual_seed(1)
+    wave = torch.randn(int(starts[-1] + lens[-1]) + 4, generator=g, device=dev) * 0.1
+    offset = torch.from_numpy(starts).to(dev)
+    length = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    db = torch.empty(plan.out_shape(n), device=dev)
+    out = plan.forward(wave, offset, length, out_db=db)
+    torch.cuda.synchronize()
+    assert out.shape == (n, 1, 128, 157) and torch.isfinite(out).all()
+    flat = out.view(n, -1).double()
+    assert flat.mean(dim=1).abs().max().item() < 1e-5
+    assert (flat.std(dim=1) - 1.0).abs().max().item() < 1e-5
+    # frames that lie entirely in the zero padding sit exactly at the floor
+    short = int(np.argmin(lens))
+    first_silent = (int(lens[short]) + 1024) // 512 + 1
+    assert (db[short, 0, :, first_silent:] == -100.0).all()
+    cfg = O.OracleConfig()
+    w = wave.cpu().numpy()
+    cropped = int(np.argmax((lens > T) & (lens < 2 * T)))
+    for i in (short, int(np.argmax(lens)), cropped, 0, n - 1):
+        ref = O.logmel(w[starts[i]:starts[i] + lens[i]], cfg)
+        assert np.abs(out[i, 0].cpu().numpy() - ref).max() < NORM_ATOL, i
