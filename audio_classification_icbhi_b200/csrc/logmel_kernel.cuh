@@ -53,6 +53,10 @@
 #ifndef LM_TIMING
 #define LM_TIMING 0
 #endif
+#ifndef LM_SKEW
+#define LM_SKEW 0   // 1: odd warps of a group apply the twiddle before barrier (A), even warps after it: the two
+                    //    halves then hit the shared-memory pipe (transposes) and the FMA pipe out of step
+#endif
 #ifndef LM_TW2
 #define LM_TW2 1   // 1: twiddle = product of two table entries (10 table rows); 0: full table (31 rows, 8 KB)
 #endif
@@ -264,8 +268,9 @@ __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __res
     }
 }
 __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
-                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
-    warp_twiddle(z, tw, lane);
+                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane,
+                                                    bool do_twiddle = true) {
+    if (do_twiddle) warp_twiddle(z, tw, lane);
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -533,6 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 }
             }
             lm_fft32_aos_from2(z);
+            if (LM_SKEW && (gw & 1)) warp_twiddle(z, s_tw, lane);
         }
         LM_T(1);   // FFT part 1
         group_bar(group);   // (A) every warp of the group is done with the mel phase of the previous item
@@ -560,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             const int lane = launder(lane_), gw = launder(gwarp_);
             float* const scr = rows + gw * kRowFloats;
             float xr[32], xi[32];
-            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane);
+            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane, !(LM_SKEW && (gw & 1)));
             const int srcl = (32 - lane) & 31;
             const bool l0 = (lane == 0);
             if (NFFT == 2048) {

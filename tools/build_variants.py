@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "audio_classification_icbhi_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "tw31": ["-DLM_TW2=0"],
+    "skew": ["-DLM_SKEW=1"],
 }
 
 def build():
