@@ -38,9 +38,33 @@ def main() -> None:
         torch.cuda.synchronize()
         assert torch.equal(full, ref), f"rank {rank}: fused gather ({fg.mode}) differs from the NCCL gather"
         modes.append(fg.mode)
+    # ---- BASELINE configs[4]: 1-hour recording, 1 s windows at 50 % overlap -> 7200 windows, sharded by index;
+    #      the recording is replicated, every rank extracts its block of windows and the blocks are gathered
+    #      in-kernel.  Rank 0 also extracts all 7200 windows alone: the gathered result must equal it bit for bit.
+    from audio_classification_icbhi_b200 import segment_offsets, shard_bounds, shard_size
+    plan1 = LogMelPlan(target_length=16000, device=dev)
+    g2 = torch.Generator(device=dev).manual_seed(2)
+    rec = torch.randn(3600 * 16000, generator=g2, device=dev) * 0.1
+    starts_np, lens_np, times = segment_offsets(int(rec.numel()), 16000, 1.0, 0.5)
+    assert len(starts_np) == 7200 and times[-1] == (3599.5, 3600.0)
+    per = shard_size(len(starts_np), world)
+    lo, hi = shard_bounds(len(starts_np), rank, world)
+    fgw = FusedGather(plan1, per)
+    fgw.full.fill_(float("nan"))
+    torch.cuda.synchronize()
+    dist.barrier()
+    fgw.run(rec, torch.from_numpy(starts_np[lo:hi]).to(dev), torch.from_numpy(lens_np[lo:hi]).to(dev))
+    allw = fgw.finish()
+    torch.cuda.synchronize()
+    if rank == 0:
+        alone = plan1.forward(rec, torch.from_numpy(starts_np).to(dev), torch.from_numpy(lens_np).to(dev))
+        torch.cuda.synchronize()
+        for r in range(world):          # shards sit at r * per; the last one may be short
+            a, b = shard_bounds(len(starts_np), r, world)
+            assert torch.equal(allw[r * per:r * per + (b - a)], alone[a:b]), f"analyzer windows of rank {r} differ"
     dist.barrier()
     if rank == 0:
-        print("FUSED_GATHER_OK", world, "ranks;", " | ".join(modes))
+        print("FUSED_GATHER_OK", world, "ranks;", " | ".join(modes), "; 7200 analyzer windows sharded and gathered")
     dist.destroy_process_group()
 
 
