@@ -440,3 +440,14 @@ def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
     y = (windows @ kernel.T).reshape(-1)                                  # block-major, phase-minor
     target = int(np.ceil(q * n / o))
     return y[:target]
+
+
+def golden_filterbank(n_fft: int = 2048) -> np.ndarray:
+    """torchaudio's own float32 filterbank for the path's two configurations (tests/golden/fb_golden.npz,
+    written by tests/golden/make_fb_golden.py), as float64 [n_freqs, n_mels]: pass it as ``fb=`` to `logmel`
+    to take the ~1e-5 restatement error of `melscale_fbanks_htk` out of a comparison."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fb_golden.npz"))
+    fb = np.zeros(tuple(g[f"{n_fft}/shape"]), dtype=np.float64)
+    fb[g[f"{n_fft}/k"], g[f"{n_fft}/m"]] = g[f"{n_fft}/v"].astype(np.float64)
+    return fb

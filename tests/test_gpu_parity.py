@@ -352,3 +352,20 @@ def test_icbhi_sized_ragged_corpus(A):
     for i in (short, int(np.argmax(lens)), cropped, 0, n - 1):
         ref = O.logmel(w[starts[i]:starts[i] + lens[i]], cfg)
         assert np.abs(out[i, 0].cpu().numpy() - ref).max() < NORM_ATOL, i
+
+
+def test_accuracy_with_the_reference_filterbank_is_at_fp32_level(A):
+    """With torchaudio's own float32 filterbank in the oracle (tests/golden/fb_golden.npz) instead of the numpy
+    restatement of melscale_fbanks, the float64 oracle isolates the arithmetic of the path: on noise-like
+    clips the CUDA mel power is within 5e-6 relative (bar: 1e-4), dB within 5e-5 (bar: 1e-3) -- the level
+    of the reference's own float32 pipeline (1.0e-6 / 4.5e-6)."""
+    plan = get_plan(A)
+    fb = O.golden_filterbank(2048)
+    rs = np.random.RandomState(11)
+    for x in (rs.standard_normal(80000) * 0.1, rs.uniform(-1, 1, 80000), rs.standard_normal(30000) * 1e-3):
+        x = x.astype(np.float32)
+        r = run_clips(plan, [x])
+        st = O.logmel(x, O.OracleConfig(), return_stages=True, fb=fb)
+        assert rel_err(r["mel_power"][0], st["mel_power"]).max() < 5e-6
+        assert np.abs(r["db"][0] - st["db"]).max() < 5e-5
+        assert np.abs(r["out"][0] - st["out"]).max() < 1e-5
