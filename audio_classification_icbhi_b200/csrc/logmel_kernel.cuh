@@ -53,6 +53,9 @@
 #ifndef LM_TIMING
 #define LM_TIMING 0
 #endif
+#ifndef LM_SILENT
+#define LM_SILENT 1   // 1: tiles that lie entirely in a plain clip's zero padding skip FFT and mel and write the floor
+#endif
 #ifndef LM_SKEW
 #define LM_SKEW 0   // 1: odd warps of a group apply the twiddle before barrier (A), even warps after it: the two
                     //    halves then hit the shared-memory pipe (transposes) and the FMA pipe out of step
@@ -336,11 +339,11 @@ struct ClipCtx {
     int shift, f0, f1, t0, t1;
     float nscale, gain;
     int plain;
-    int pad_;
+    int silent_from;     // first tile that lies entirely in the zero padding (n_tiles if none); plain clips only
 };
 static_assert(sizeof(ClipCtx) <= 64, "ClipCtx slot size");
 
-__device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* __restrict__ c) {
+__device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* __restrict__ c, int nfft) {
     const long long off = p.offset[clip];
     const int len = p.length[clip];
     const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
@@ -358,6 +361,23 @@ __device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* _
     c->nscale = nscale; c->gain = gain; c->seed = seed;
     c->nz = (p.noise != nullptr && nscale != 0.0f) ? p.noise + static_cast<size_t>(clip) * p.T : nullptr;
     c->plain = (shift == 0) && (nscale == 0.0f) && (gain == 1.0f);
+    // A tile is silent when every sample it touches -- reflect padding included -- lies in the zero padding of a
+    // plain clip: its power spectrum is exactly 0 and every feature sits at the dB floor, so FFT and mel are
+    // skipped (ICBHI cycles average 2.7 s of the 5 s target).  Silence is monotone in the tile index.
+    int silent_from = p.n_tiles;
+    if (LM_SILENT && c->plain) {
+        const int tile_f = (nfft == 2048) ? 8 : 16;
+        for (int t = p.n_tiles - 1; t >= 0; --t) {
+            const int tf = t * tile_f;
+            const int nf = (p.frames - tf) < tile_f ? (p.frames - tf) : tile_f;
+            const int j0 = tf * p.hop - nfft / 2, j1 = j0 + (nf - 1) * p.hop + nfft - 1;   // first / last padded-signal index
+            int lowest = j0 < 0 ? 0 : j0;                                                  // lowest clip index the tile reads
+            if (j1 >= p.T) { const int r = 2 * (p.T - 1) - j1; lowest = r < lowest ? r : lowest; }
+            if (c->lc > lowest) break;
+            silent_from = t;
+        }
+    }
+    c->silent_from = silent_from;
 }
 
 template <int NFFT, bool EXTRA_OUT>
@@ -441,8 +461,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }
         *s_pend = (cnt != 0);
     };
+    auto tile_silent = [&](const ClipCtx* __restrict__ c, int tile_) -> bool {   // group-uniform
+        return LM_SILENT && tile_ >= c->silent_from;
+    };
     // returns (group-uniform) whether anything was written
     auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_) -> bool {   // all threads of the group
+        if (tile_silent(cc, tile_)) return false;   // nobody will read the buffer
         int e_lo, cnt;
         bulk_range(cc, tile_, e_lo, cnt);
         const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
@@ -478,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     // ---- prologue: item 0 is staged before the loop; item it+1 is staged during item it ----------------
     const int cstride = nv;
     if (gtid == 0) {
-        load_clip(p, clip0, &s_ctx[0]);
+        load_clip(p, clip0, &s_ctx[0], NFFT);
         stage_bulk(&s_ctx[0], 0);
     }
     group_bar(group);
@@ -509,6 +533,48 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
         // ---- window + first butterfly stage + rest of FFT part 1 (registers; reads the staged samples) ----
         // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
+        // item it+1: its TMA part goes into the buffer consumed by (A); one thread; the clip's context slot is
+        // filled when its first tile comes up
+        const bool has1 = (it + 1 < n_items);
+        int tile1 = tile + 1, ord1 = ord;
+        if (tile1 == p.n_tiles) { tile1 = 0; ++ord1; }
+        auto issue_next = [&]() {
+            if (has1 && gtid == 0) {
+                if (tile1 == 0) load_clip(p, clip0 + ord1 * cstride, &s_ctx[ord1 & 1], NFFT);
+                stage_bulk(&s_ctx[ord1 & 1], tile1);
+            }
+        };
+        if (__builtin_expect(tile_silent(&s_ctx[ord & 1], tile), 0)) {
+            group_bar(group);   // (A)
+            issue_next();
+            group_bar(group);   // (B)
+            // ---- silent tile: every feature is the floor (or a mask's 0) ----------------------------------------
+            const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+            const ClipCtx* __restrict__ cx = &s_ctx[ord & 1];
+            float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+            float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+            const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
+            float ssum = 0.0f, qsum = 0.0f;
+            for (int idx = gtid; idx < n_mels * TILE_F; idx += kGroupThreads) {
+                const int m = idx / TILE_F, f = idx - m * TILE_F, tt = tf + f;
+                if (f < nf) {
+                    const float v = ((m >= cf0 && m < cf1) || (tt >= ct0 && tt < ct1)) ? 0.0f : p.floor_db;
+                    const int o = m * frames + tt;
+                    out[o] = v;
+                    if (EXTRA_OUT) {
+                        if (odb) odb[o] = v;
+                        if (omp) omp[o] = 0.0f;
+                    }
+                    ssum += v;
+                    qsum = fmaf(v, v, qsum);
+                }
+            }
+            double2 st = s_stat[tid];
+            st.x += static_cast<double>(ssum);
+            st.y += static_cast<double>(qsum);
+            s_stat[tid] = st;
+        } else {
         lm_f2 z[32];
         if (LM_EXP != 2) {
             const int lane = launder(lane_), gw = launder(gwarp_);
@@ -545,15 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                             //     (rows are free) and with this item's staged samples (buffer is free)
 
         LM_T(2);   // barrier A
-        // ---- item it+1: its TMA part goes into the buffer just consumed; one thread; the clip's context
-        //      slot is filled when its first tile comes up ----------------------------------------------
-        const bool has1 = (it + 1 < n_items);
-        int tile1 = tile + 1, ord1 = ord;
-        if (tile1 == p.n_tiles) { tile1 = 0; ++ord1; }
-        if (has1 && gtid == 0) {
-            if (tile1 == 0) load_clip(p, clip0 + ord1 * cstride, &s_ctx[ord1 & 1]);
-            stage_bulk(&s_ctx[ord1 & 1], tile1);
-        }
+        issue_next();
 
         // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
         if (LM_EXP == 3) {
@@ -716,6 +774,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             s_stat[tid] = st;
         }
 
+        }   // not silent
         LM_T(5);   // mel phase
         // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
         if (has1) {

@@ -369,3 +369,36 @@ def test_accuracy_with_the_reference_filterbank_is_at_fp32_level(A):
         assert rel_err(r["mel_power"][0], st["mel_power"]).max() < 5e-6
         assert np.abs(r["db"][0] - st["db"]).max() < 5e-5
         assert np.abs(r["out"][0] - st["out"]).max() < 1e-5
+
+
+def test_silent_tiles_of_short_clips(A):
+    """Tiles that lie entirely in a plain clip's zero padding skip FFT and mel (silent_from in the clip context):
+    mel power exactly 0 and dB exactly the floor there, masks still applied, statistics (hence the normalised
+    output) as if they had been computed; rolled / noisy / gained clips of the same length take the full path."""
+    plan = get_plan(A)
+    rs = np.random.RandomState(21)
+    lens = [0, 1, 3000, 20000, 41000, 79000, 80000]
+    clips = [(rs.standard_normal(n) * 0.1).astype(np.float32) for n in lens]
+    aug = A.make_aug_array(len(clips))
+    aug["f0"], aug["f1"], aug["t0"], aug["t1"] = 10, 21, 100, 131          # masks only: the clips stay "plain"
+    r = run_clips(plan, clips, aug=aug)
+    cfg = O.OracleConfig()
+    for i, x in enumerate(clips):
+        st = O.logmel(x, cfg, return_stages=True, masks=(10, 21, 100, 131), fb=O.golden_filterbank(2048))
+        assert np.abs(r["out"][i] - st["out"]).max() < NORM_ATOL, lens[i]
+        assert np.abs(r["db"][i] - st["db"]).max() < DB_ATOL, lens[i]
+        first_silent = (lens[i] + 1024) // 512 + 1                            # first frame that sees no sample
+        if first_silent < 157:
+            tail_db, tail_mp = r["db"][i][:, first_silent:], r["mel_power"][i][:, first_silent:]
+            assert (tail_mp == 0.0).all()
+            expect = np.full_like(tail_db, -100.0)
+            expect[10:21, :] = 0.0
+            lo = max(100 - first_silent, 0)
+            expect[:, lo:max(131 - first_silent, 0)] = 0.0
+            np.testing.assert_array_equal(tail_db, expect)
+    # the same short clip with a roll is not plain: full path, still equal to the oracle
+    aug2 = A.make_aug_array(1)
+    aug2["shift"] = 5000
+    r2 = run_clips(plan, [clips[3]], aug=aug2)
+    ref2 = O.logmel(clips[3], cfg, shift=5000, fb=O.golden_filterbank(2048))
+    assert np.abs(r2["out"][0] - ref2).max() < NORM_ATOL
