@@ -230,3 +230,41 @@ def test_load_audio_resamples_on_the_gpu(tmp_path):
     assert np.abs(w[0].numpy() - O.resample(q, 4000, 16000)).max() < 2e-6
     feats = p.preprocess(path)
     assert feats.shape == (1, 128, 157)
+
+
+def test_randomised_geometries_match_oracle():
+    """Seeded sweep over plan geometries (n_fft, hop, n_mels, target length down to just above n_fft/2, i.e. one
+    or two tiles, a last tile with a single frame, ...) and ragged clip lengths (empty, shorter than a hop,
+    cropped), several clips per group: the kernel against the oracle fed with torchaudio's filterbank."""
+    rs = np.random.RandomState(2024)
+    for trial in range(14):
+        n_fft = int(rs.choice([2048, 2048, 1024]))
+        hop = int(rs.choice([64, 128, 160, 256, 400, 512])) if n_fft == 2048 else int(rs.choice([64, 100, 128, 256]))
+        n_mels = int(rs.choice([24, 40, 64, 80, 128, 136, 256 if n_fft == 2048 else 96]))
+        T = int(rs.choice([n_fft // 2 + 1, n_fft // 2 + 7, n_fft, 3000, 7 * hop + 5, 8 * hop, 8 * hop - 1, 16001, 48000]))
+        T = max(T, n_fft // 2 + 1)
+        plan = A.LogMelPlan(n_fft=n_fft, hop_length=hop, n_mels=n_mels, target_length=T, device="cuda:0")
+        plan.set("max_ctas", int(rs.choice([1, 2, 148])))
+        cfg = O.OracleConfig(n_mels=n_mels, n_fft=n_fft, hop_length=hop, duration=T / 16000.0)
+        assert cfg.target_length == T or abs(cfg.target_length - T) <= 1
+        lens = [0, 1, hop - 1, T, T + 1, 3 * T + 11] + [int(v) for v in rs.randint(1, 2 * T, 5)]
+        clips = [(rs.standard_normal(n) * 0.1).astype(np.float32) for n in lens]
+        starts, pos = [], 0
+        for c in clips:
+            starts.append(pos)
+            pos += (len(c) + 3) // 4 * 4 + (4 if trial % 2 else 1)      # every other trial: unaligned starts
+        packed = np.zeros(pos + 4, dtype=np.float32)
+        for s, c in zip(starts, clips):
+            packed[s:s + len(c)] = c
+        dev = plan.device
+        out = plan.forward(torch.from_numpy(packed).to(dev), torch.tensor(starts, dtype=torch.int64, device=dev),
+                           torch.tensor(lens, dtype=torch.int32, device=dev)).cpu().numpy()[:, 0]
+        fb = A.reference_filterbank(n_fft // 2 + 1, n_mels, 16000).numpy().astype(np.float64)
+        frames = 1 + T // hop
+        assert out.shape == (len(clips), n_mels, frames), (trial, out.shape)
+        for i, c in enumerate(clips):
+            w = O.pad_or_crop(c.astype(np.float64), T)
+            db = O.amplitude_to_db(O.mel_power(O.stft_power(w, n_fft, hop), fb))
+            ref = O.normalize(db)
+            assert np.abs(out[i] - ref).max() < NORM_ATOL, (trial, n_fft, hop, n_mels, T, lens[i])
+        plan.close()
