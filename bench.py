@@ -282,6 +282,48 @@ def run_b200(args) -> None:
     pcm_ok = bool(torch.equal(host_out, pcm_ref.cpu()))
     del pcm_ref
 
+    # ---- the other BASELINE configs on one GPU, device-resident (secondary figures, rank 0 of a 1-GPU run) ------
+    extra = {}
+    if world == 1:
+        import numpy as np
+        # configs[2]: ICBHI-sized ragged corpus, 6900 cycles of lognormal length, pad / crop to 5 s
+        rs = np.random.RandomState(0)
+        secs = np.clip(rs.lognormal(np.log(2.5), 0.5, 6900), 0.2, 16.2)
+        lens = (secs * 16000).astype(np.int64)
+        starts = np.concatenate([[0], np.cumsum((lens + 3) // 4 * 4)[:-1]])
+        g = torch.Generator(device=dev).manual_seed(1)
+        rwave = torch.randn(int(starts[-1] + lens[-1]) + 4, generator=g, device=dev) * 0.1
+        roff, rlen = torch.from_numpy(starts).to(dev), torch.from_numpy(lens.astype(np.int32)).to(dev)
+        rout = torch.empty(plan.out_shape(6900), device=dev)
+
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        ms_r = timed(lambda: plan.forward(rwave, roff, rlen, out=rout))
+        extra["ragged_corpus"] = {"workload": "configs[2]: 6900 cycles, lognormal 0.2-16.2 s (mean %.2f s), pad/crop to 5 s" % secs.mean(),
+                                  "ms": ms_r, "clips_per_s": 6900 / ms_r * 1e3}
+        del rwave, rout
+        # configs[4]: 1-hour recording, 1 s windows at 50 % overlap -> 7200 windows (offsets into one buffer)
+        from audio_classification_icbhi_b200 import segment_offsets
+        plan_w = LogMelPlan(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=128, target_length=16000, device=dev)
+        rec = torch.randn(3600 * 16000, generator=g, device=dev) * 0.1
+        ws, wl, _ = segment_offsets(int(rec.numel()), 16000, 1.0, 0.5)
+        woff, wlen = torch.from_numpy(ws).to(dev), torch.from_numpy(wl).to(dev)
+        wout = torch.empty(plan_w.out_shape(len(ws)), device=dev)
+        ms_w = timed(lambda: plan_w.forward(rec, woff, wlen, out=wout))
+        extra["analyzer_windows"] = {"workload": "configs[4]: 1 h @ 16 kHz, 1 s windows, 50 % overlap -> 7200 windows [7200,1,128,32]",
+                                     "ms": ms_w, "windows_per_s": len(ws) / ms_w * 1e3, "audio_seconds_per_s": 3600.0 / (ms_w * 1e-3)}
+        del rec, wout, plan_w
+
     # ---- optional: features all-gathered to every rank (single consumer) -----------------------
     gathered = None
     if world > 1:
@@ -365,6 +407,7 @@ def run_b200(args) -> None:
                        "smem_bytes": info["smem_bytes"], "tma_staging": info["tma_staging"]},
             "result_checksum": checksum,
         }
+        line.update(extra)
         if gathered:
             line["gathered"] = gathered
         print(json.dumps(line), flush=True)
