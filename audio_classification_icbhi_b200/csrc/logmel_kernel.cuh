@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         e_lo = lo;
         cnt = (hi - lo) & ~3;
     };
+    auto tile_silent = [&](const ClipCtx* __restrict__ c, int tile_) -> bool {   // group-uniform
+        return LM_SILENT && tile_ >= c->silent_from;
+    };
     auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_) {   // ONE thread of the group
         int e_lo, cnt;
         bulk_range(c, tile_, e_lo, cnt);
@@ -459,10 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             mbar_expect_tx(mbar, static_cast<uint32_t>(cnt) * 4u);
             bulk_g2s(sb + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u, mbar);
         }
-        *s_pend = (cnt != 0);
-    };
-    auto tile_silent = [&](const ClipCtx* __restrict__ c, int tile_) -> bool {   // group-uniform
-        return LM_SILENT && tile_ >= c->silent_from;
+        *s_pend = (cnt != 0 ? 1 : 0) | (tile_silent(c, tile_) ? 2 : 0);   // bit 0: bulk copy pending, bit 1: silent tile
     };
     // returns (group-uniform) whether anything was written
     auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_) -> bool {   // all threads of the group
@@ -525,7 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     for (int it = 0; it < n_items; ++it) {
         const int tf = tile * TILE_F;                  // first frame of the tile
         const int clip = clip0 + ord * cstride;
-        if (*s_pend) {
+        const int st_item = *s_pend;
+        if (st_item & 1) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
         }
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 stage_bulk(&s_ctx[ord1 & 1], tile1);
             }
         };
-        if (__builtin_expect(tile_silent(&s_ctx[ord & 1], tile), 0)) {
+        if (__builtin_expect((st_item & 2) != 0, 0)) {
             group_bar(group);   // (A)
             issue_next();
             group_bar(group);   // (B)
