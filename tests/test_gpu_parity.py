@@ -402,3 +402,30 @@ def test_silent_tiles_of_short_clips(A):
     r2 = run_clips(plan, [clips[3]], aug=aug2)
     ref2 = O.logmel(clips[3], cfg, shift=5000, fb=O.golden_filterbank(2048))
     assert np.abs(r2["out"][0] - ref2).max() < NORM_ATOL
+
+
+def test_forward_is_cuda_graph_capturable(A):
+    """lm_forward allocates nothing and only enqueues on the caller's stream, so a serving loop can capture it
+    in a CUDA graph: replaying the graph on new samples in the same buffers gives the eager result bit for bit."""
+    plan = get_plan(A)
+    dev = plan.device
+    B, T = 64, 80000
+    g = torch.Generator(device=dev).manual_seed(9)
+    clips = torch.randn(B, T, generator=g, device=dev) * 0.1
+    offset = torch.arange(B, device=dev, dtype=torch.int64) * T
+    length = torch.full((B,), T, device=dev, dtype=torch.int32)
+    out = torch.empty(plan.out_shape(B), device=dev)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        plan.forward(clips.view(-1), offset, length, out=out)       # warm-up outside the capture
+    torch.cuda.current_stream(dev).wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan.forward(clips.view(-1), offset, length, out=out)
+    clips.copy_(torch.randn(B, T, generator=g, device=dev) * 0.1)    # new samples, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    eager = plan.forward(clips.view(-1), offset, length)
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
