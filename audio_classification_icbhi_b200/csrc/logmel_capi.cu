@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -28,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr int kSlots = 3;   // host pipeline depth
+constexpr int kCounters = 64;   // launches of one plan that may be in flight at once (on any streams)
 
 struct HostSlot {
     cudaStream_t stream = nullptr;
@@ -62,7 +64,8 @@ struct lm_plan {
     // host pipeline
     HostSlot slots[kSlots];
     bool slots_ready = false;
-    long long launches = 0;
+    std::atomic<long long> launches{0};
+    int* d_counters = nullptr;   // kCounters work counters for the kernel's dynamic clip scheduling, one per launch in flight
 };
 
 namespace {
@@ -70,7 +73,7 @@ namespace {
 int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab); cudaFree(p->d_counters);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_pcm); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -103,6 +106,9 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     k.wave = wave; k.offset = reinterpret_cast<const long long*>(offset); k.length = length;
     k.aug = aug; k.noise = noise; k.out_norm = out_norm; k.out_db = out_db; k.out_melpow = out_melpow;
     k.B = B; k.normalize = normalize;
+    const long long seq = p->launches.fetch_add(1);
+    k.work_counter = p->d_counters + (seq % kCounters);
+    LM_CUDA(cudaMemsetAsync(k.work_counter, 0, sizeof(int), stream));
     const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
     const int grid = std::min<int>(B, cap);
     const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
@@ -114,7 +120,6 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
         else lm::logmel_kernel<1024, false><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
     }
     LM_CUDA(cudaGetLastError());
-    ++p->launches;
     return LM_OK;
 }
 
@@ -287,7 +292,9 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
         (rc = up(reinterpret_cast<void**>(&p->d_tw), tw.data(), sizeof(float2) * tw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float4) * melw.size())) ||
-        (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab)))) {
+        (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab))) ||
+        (rc = (cudaMalloc(&p->d_counters, sizeof(int) * kCounters) == cudaSuccess &&
+               cudaMemset(p->d_counters, 0, sizeof(int) * kCounters) == cudaSuccess) ? LM_OK : cuda_fail(cudaGetLastError(), "work counters"))) {
         free_plan(p);
         return rc;
     }
@@ -353,7 +360,7 @@ int lm_plan_set(lm_plan* plan, const char* key, int value) {
     return LM_ERR_INVALID_ARG;
 }
 
-int64_t lm_plan_launch_count(const lm_plan* plan) { return plan ? plan->launches : 0; }
+int64_t lm_plan_launch_count(const lm_plan* plan) { return plan ? plan->launches.load() : 0; }
 
 int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
                const lm_aug* aug, const float* noise, float* out_norm, float* out_db, float* out_melpow,
@@ -602,7 +609,7 @@ static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, in
             e = cudaMemcpyAsync(s.d_pcm, pcm + lo, sizeof(int16_t) * n_wave, cudaMemcpyHostToDevice, s.stream);
             if (e == cudaSuccess) {
                 if ((rc = lm_pcm16_decode(s.d_pcm, s.d_wave, static_cast<int64_t>(n_wave), s.stream))) break;
-                ++plan->launches;
+                plan->launches.fetch_add(1);
             }
         }
         if (e == cudaSuccess && noise)

@@ -114,6 +114,10 @@ struct KParams {
     float* peer[kMaxPeers];
     int n_peer;
     float* mc_out;
+    // dynamic clip scheduling: clips [0, 2*gridDim) are dealt statically (one per group); every further clip
+    // is fetched with atomicAdd on this counter (zeroed by the host before the launch) when a group starts the
+    // last tile of its current clip, so that ragged batches (unequal numbers of silent tiles) stay balanced
+    int* work_counter;
     // plan
     int T, hop, frames, n_mels, n_tiles;
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
@@ -314,7 +318,7 @@ struct Smem {
     static constexpr size_t kRed = kBar + 32;                            // per group: reduction scratch + broadcast
     static constexpr size_t kRedGroup = sizeof(double) * 2 * kGroupWarps + 16;
     static constexpr size_t kCtx = kRed + kGroups * kRedGroup;           // per group two ClipCtx slots (ordinal & 1)
-    static constexpr size_t kTab = kCtx + kGroups * 2 * 64;
+    static constexpr size_t kTab = kCtx + kGroups * 2 * 80;
     static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fp64 (sum, sumsq)
     static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
     static constexpr size_t kTw = kWin + sizeof(float) * (NFFT / 2);     // first half of the window
@@ -331,7 +335,7 @@ struct Smem {
 // Everything the staging and epilogue code needs to know about one clip.  Two slots per group live
 // in shared memory (clip ordinal & 1: staging runs one item ahead of the epilogue) so that none of
 // it occupies registers across the FFT.
-struct ClipCtx {
+struct alignas(16) ClipCtx {
     const float* src;    // first sample after the centre crop
     const float* nz;     // host-drawn noise row or nullptr
     uint64_t seed;
@@ -340,13 +344,17 @@ struct ClipCtx {
     float nscale, gain;
     int plain;
     int silent_from;     // first tile that lies entirely in the zero padding (n_tiles if none); plain clips only
+    int clip;            // index of the clip in the batch; -1 in the "next clip" slot = the batch is exhausted
+    int pad_;
 };
-static_assert(sizeof(ClipCtx) <= 64, "ClipCtx slot size");
+constexpr int kCtxSlot = 80;
+static_assert(sizeof(ClipCtx) <= kCtxSlot && kCtxSlot % 16 == 0, "ClipCtx slot size");
 
 __device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* __restrict__ c, int nfft) {
     const long long off = p.offset[clip];
     const int len = p.length[clip];
     const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
+    c->clip = clip;
     c->lc = len < p.T ? len : p.T;
     c->src = p.wave + off + crop;
     int shift = 0, f0 = 0, f1 = 0, t0 = 0, t1 = 0;
@@ -425,10 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     // ---- this group's clips -----------------------------------------------------------------------
     const int nv = static_cast<int>(gridDim.x) * kGroups;
-    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-    const int n_my = (p.B - clip0 + nv - 1) / nv;
-    if (n_my <= 0) return;
-    const int n_items = n_my * p.n_tiles;
+    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);   // first clip: static
+    if (clip0 >= p.B) return;
 
     const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
     const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
@@ -500,7 +506,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     };
 
     // ---- prologue: item 0 is staged before the loop; item it+1 is staged during item it ----------------
-    const int cstride = nv;
     if (gtid == 0) {
         load_clip(p, clip0, &s_ctx[0], NFFT);
         stage_bulk(&s_ctx[0], 0);
@@ -515,16 +520,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     uint32_t parity = 0;                   // mbarrier phase of the staging buffer (group-uniform)
     s_stat[tid] = make_double2(0.0, 0.0);  // this thread's running (sum, sum of squares) of the clip's dB values
-    int tile = 0, ord = 0;                 // tile index and clip ordinal of item `it`
+    int tile = 0, ord = 0, clip = clip0;   // tile index, clip ordinal (context slot = ord & 1) and clip index of the item
 
 #if LM_TIMING
     long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = clock64();
 #endif
 #pragma unroll 1
-    for (int it = 0; it < n_items; ++it) {
+    for (;;) {
         const int tf = tile * TILE_F;                  // first frame of the tile
-        const int clip = clip0 + ord * cstride;
         const int st_item = *s_pend;
         if (st_item & 1) {
             mbar_wait(mbar, parity);
@@ -536,13 +540,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
         // item it+1: its TMA part goes into the buffer consumed by (A); one thread; the clip's context slot is
         // filled when its first tile comes up
-        const bool has1 = (it + 1 < n_items);
         int tile1 = tile + 1, ord1 = ord;
         if (tile1 == p.n_tiles) { tile1 = 0; ++ord1; }
         auto issue_next = [&]() {
-            if (has1 && gtid == 0) {
-                if (tile1 == 0) load_clip(p, clip0 + ord1 * cstride, &s_ctx[ord1 & 1], NFFT);
-                stage_bulk(&s_ctx[ord1 & 1], tile1);
+            if (gtid == 0) {
+                ClipCtx* const cn = &s_ctx[ord1 & 1];
+                if (tile1 == 0) {   // last tile of this clip: fetch the group's next clip
+                    const int nxt = nv + atomicAdd(p.work_counter, 1);
+                    if (nxt < p.B) {
+                        load_clip(p, nxt, cn, NFFT);
+                        stage_bulk(cn, 0);
+                    } else {
+                        cn->clip = -1;
+                    }
+                } else {
+                    stage_bulk(cn, tile1);
+                }
             }
         };
         if (__builtin_expect((st_item & 2) != 0, 0)) {
@@ -778,6 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }   // not silent
         LM_T(5);   // mel phase
         // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
+        const bool has1 = (tile1 != 0) || (s_ctx[ord1 & 1].clip >= 0);   // written before (B) by thread 0
         if (has1) {
             if (stage_gather(&s_ctx[ord1 & 1], tile1)) group_bar(group);   // (C) only for tiles that touch a clip edge
         }
@@ -838,7 +852,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 for (int i = (n4 << 2) + gtid; i < static_cast<int>(clip_elems); i += kGroupThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;
             }
+            if (!has1) break;
             s_stat[tid] = make_double2(0.0, 0.0);
+            clip = s_ctx[ord1 & 1].clip;
             tile = 0;
             ++ord;
         } else {
