@@ -27,8 +27,10 @@
  * Conventions
  *   - every function returns LM_OK (0) or a negative lm_status; nothing throws across the ABI.
  *   - lm_forward allocates nothing, enqueues on the caller's stream and does not synchronise.
- *   - a plan is immutable after creation: concurrent lm_forward calls on different streams
- *     are safe.  lm_forward_host uses plan-owned staging buffers and streams and is NOT
+ *   - a plan's tables are immutable after creation: concurrent lm_forward calls on different streams
+ *     are safe (each launch takes one of 64 plan-owned work counters, zeroed on the caller's stream
+ *     right before the kernel: keep fewer than 64 launches of one plan in flight; a launch captured
+ *     in a CUDA graph keeps its counter, so do not replay it concurrently with itself).  lm_forward_host uses plan-owned staging buffers and streams and is NOT
  *     re-entrant on one plan.
  *   - there is no CPU fallback anywhere: without a CUDA device lm_plan_create fails.
  */
