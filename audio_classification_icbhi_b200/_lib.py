@@ -68,6 +68,8 @@ EXPORTS = {
     "lm_resampler_destroy": (C.c_int, [C.c_void_p]),
     "lm_resampler_out_len": (C.c_int64, [C.c_void_p, C.c_int64]),
     "lm_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lm_resample_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
     "lm_forward_host_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
 }

@@ -119,11 +119,15 @@ __global__ void pcm16_decode_kernel(const int16_t* __restrict__ in, float* __res
 // torchaudio runs that as a dense conv1d; all but ~2 width + 1 taps of a phase are (numerically) zero, so
 // the host keeps, per phase, the window of `ntaps` taps around the phase's centre and the kernel walks only
 // those.  One output sample per thread; a block's outputs share their input span through L1.
-__global__ void resample_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out,
+// grid.y = row (channel / clip): rows of equal length `n_in`, `in_stride` / `out_stride` floats apart
+__global__ void resample_kernel(const float* __restrict__ x_all, long long n_in, long long in_stride,
+                                float* __restrict__ y_all, long long n_out, long long out_stride,
                                 const float* __restrict__ taps, const int* __restrict__ k0, int o, int q, int ntaps,
                                 int width) {
     const long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n_out) return;
+    const float* __restrict__ x = x_all + static_cast<long long>(blockIdx.y) * in_stride;
+    float* __restrict__ y = y_all + static_cast<long long>(blockIdx.y) * out_stride;
     const long long m = j / q;
     const int p = static_cast<int>(j - m * q);
     const float* __restrict__ w = taps + static_cast<size_t>(p) * ntaps;

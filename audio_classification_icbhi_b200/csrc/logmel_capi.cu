@@ -501,18 +501,28 @@ int64_t lm_resampler_out_len(const lm_resampler* r, int64_t in_len) {
     return (static_cast<int64_t>(r->neu) * in_len + r->orig - 1) / r->orig;   // ceil(new * len / orig)
 }
 
-int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* out, void* cuda_stream) {
-    if (!r || in_len < 0) return LM_ERR_INVALID_ARG;
+int lm_resample_rows(const lm_resampler* r, const float* in, int64_t in_len, int64_t in_stride, int32_t n_rows,
+                     float* out, int64_t out_stride, void* cuda_stream) {
+    if (!r || in_len < 0 || n_rows < 0) return LM_ERR_INVALID_ARG;
     const int64_t n_out = lm_resampler_out_len(r, in_len);
-    if (n_out == 0) return LM_OK;
-    if (!in || !out) return LM_ERR_INVALID_ARG;
+    if (n_out == 0 || n_rows == 0) return LM_OK;
+    if (!in || !out || in_stride < in_len || out_stride < n_out) return LM_ERR_INVALID_ARG;
     const int threads = 256;
     const long long blocks = (n_out + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return LM_ERR_INVALID_ARG;
-    lm::resample_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-        in, in_len, out, n_out, r->d_taps, r->d_k0, r->orig, r->neu, r->ntaps, r->width);
+    for (int32_t r0 = 0; r0 < n_rows; r0 += 65535) {   // grid.y limit
+        const int32_t nr = std::min<int32_t>(65535, n_rows - r0);
+        lm::resample_kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(nr)), threads, 0,
+                              static_cast<cudaStream_t>(cuda_stream)>>>(
+            in + static_cast<int64_t>(r0) * in_stride, in_len, in_stride, out + static_cast<int64_t>(r0) * out_stride, n_out,
+            out_stride, r->d_taps, r->d_k0, r->orig, r->neu, r->ntaps, r->width);
+    }
     LM_CUDA(cudaGetLastError());
     return LM_OK;
+}
+
+int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* out, void* cuda_stream) {
+    return lm_resample_rows(r, in, in_len, in_len, 1, out, lm_resampler_out_len(r, in_len), cuda_stream);
 }
 
 int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream) {

@@ -58,9 +58,8 @@ class Resampler:
         n_out = self.out_len(n_in)
         y = torch.empty((flat.shape[0], n_out), dtype=torch.float32, device=self.device)
         s = torch.cuda.current_stream(self.device)
-        for c in range(flat.shape[0]):
-            _lib.check(self._lib.lm_resample(self._h, flat[c].data_ptr(), int(flat.shape[1]), y[c].data_ptr(),
-                                             C.c_void_p(s.cuda_stream)))
+        _lib.check(self._lib.lm_resample_rows(self._h, flat.data_ptr(), n_in, n_in, rows, y.data_ptr(), n_out,
+                                              C.c_void_p(s.cuda_stream)))
         return y.view(x.shape[:-1] + (n_out,))
 
 

@@ -168,6 +168,10 @@ int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resa
 int lm_resampler_destroy(lm_resampler* r);
 int64_t lm_resampler_out_len(const lm_resampler* r, int64_t in_len);
 int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* out, void* cuda_stream);
+/* n_rows waveforms of equal length (channels of a file, clips of a batch) in one launch; row i starts at
+ * in + i * in_stride and goes to out + i * out_stride (strides in floats). */
+int lm_resample_rows(const lm_resampler* r, const float* in, int64_t in_len, int64_t in_stride, int32_t n_rows,
+                     float* out, int64_t out_stride, void* cuda_stream);
 
 /*
  * 16-bit PCM -> fp32 in [-1, 1): x / 32768, what torchaudio.load(normalize=True) hands the reference for a
