@@ -1,13 +1,13 @@
 // logmel_kernel.cuh -- the fused log-mel kernel for sm_100a (B200).
 //
 // One persistent CTA per SM, 16 warps = TWO INDEPENDENT GROUPS of 8 warps.  A group is a
-// "virtual CTA": it owns whole clips (virtual index = group * gridDim.x + blockIdx.x, stride
-// 2 * gridDim.x), walks their (clip, tile) items on its own, and synchronises only with itself
+// "virtual CTA": it owns whole clips, one at a time (the first 2 * gridDim clips are dealt statically,
+// every further one is fetched with atomicAdd on a per-launch work counter, so ragged batches stay
+// balanced), walks the clip's (clip, tile) items on its own, and synchronises only with itself
 // (named barrier 1 + group, mbarrier [group]).  The groups share the constant tables in shared
-// memory and nothing else.  Group 1 starts half an item late, so that one group's FFT phase
-// (FMA-pipe bound) overlaps the other's mel phase (tensor pipe + shared-memory loads + epilogue):
-// within a group every warp is in the same phase, and a CTA made of one group leaves each pipe idle
-// half of the time.
+// memory and nothing else; two of them keep the scheduler's dispatch port busier than one 16-warp
+// CTA whose warps all sit in the same phase (the relative phase of the groups
+// does not matter, `stagger_ns` is kept as an experiment knob only).
 //
 // A tile is 8 frames (16 for n_fft = 1024); one warp = one frame.  Per item, inside a group:
 //
@@ -28,12 +28,16 @@
 //           A = [8 mels x {hi, lo}] x 8 bins (the 16 MMA rows hold the TF32 head and the residual
 //           of the same 8 filters), B = 8 bins x 8 frames of the power rows, once with the head
 //           and once with the residual of the power: 2 MMAs per 8 bins give all four partial
-//           products, error ~2^-19.  Only the band of bins the 8 filters touch is walked
+//           products, error ~2^-21.  Only the band of bins the 8 filters touch is walked
 //           (TA/transforms/_transforms.py:417).  Epilogue in registers: 10*log10(max(x, amin))
 //           (TA/functional/functional.py:390-391), SpecAugment intervals (:939-953), store,
 //           fp64 sum / sum-of-squares.
+//   silent  tiles that lie entirely in a plain clip's zero padding skip all of the above and write the floor /
+//           mask values and their statistics directly (bit-identical to the full path on a zero spectrum).
 //   norm    when the clip is finished the same group re-reads its (L2-resident) dB block and
-//           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116).
+//           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116); for lm_forward_gather
+//           the same pass also stores the result into the other ranks' gathered buffers (multimem.st
+//           through the NVSwitch, or plain stores to peer-mapped memory).
 //
 // Algorithmic HBM bytes per clip: 4*min(len, T) read + 4*n_mels*frames written.
 #pragma once
