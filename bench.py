@@ -10,6 +10,10 @@ over that batch = one launch of the fused kernel.  With N > 1 every rank owns it
 (clips shard by index, no data-path collective): weak scaling, value = all ranks' clips / max
 time over ranks.  The optional NCCL all-gather of the features is timed separately ("gathered").
 
+Extra keys of the line: `e2e` (lm_forward_host, pinned fp32 host buffers in, host features out),
+`e2e_pcm16` (the same clips as 16-bit PCM), `ragged_corpus` and `analyzer_windows` (BASELINE configs[2]
+and [4] on one GPU, device-resident), `gathered` (N > 1: NCCL all-gather and the in-kernel fused gather).
+
 `--impl reference` times the reference's CPU implementation of the same path (the torchaudio
 glue in oracle/torchaudio_port.py, all host threads) on a bounded sample of the same workload.
 """
@@ -391,7 +395,7 @@ def run_b200(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "fp32 FFT issue-bound, not HBM-bound: see DESIGN.md section 5"},
+                         "note": "not HBM-bound: the fp32 FFT runs at ~75 % of the schedulers' dispatch bound, 44 % of the fp32 issue peak (DESIGN.md section 5)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(BATCH * T_LEN * 4 + BATCH * 12),
                     "d2h_bytes_per_step": int(out.numel() * 4), "steps": e2e_steps, "matches_device_path": e2e_ok,
