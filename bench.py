@@ -113,6 +113,32 @@ class ClockSampler(threading.Thread):
                 "reasons": [n for b, n in names.items() if mask & b], "samples": len(used)}
 
 
+def pin_to_gpu_numa_node(index: int):
+    """Restrict this process to the CPUs NVML reports as local to the GPU, so that first-touch places the pinned
+    host buffers on the GPU's NUMA node (with 8 ranks on a 2-socket host the remote half otherwise halves the
+    end-to-end rate).  Returns the number of CPUs kept, or None if NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        phys = index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                phys = int(vis.split(",")[index])
+            except Exception:
+                phys = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -199,6 +225,9 @@ def run_b200(args) -> None:
         raise SystemExit("bench.py: no CUDA device; the log-mel path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # multi-rank runs: pinned host buffers of the e2e legs land next to this GPU's PCIe root.  Not at N = 1, where
+    # the CPU baseline of the same process must keep every host core.
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -405,6 +434,7 @@ def run_b200(args) -> None:
                           "matches_device_path_on_decoded_samples": pcm_ok,
                           "api": "lm_forward_host_pcm16: the clips as int16 PCM (wav sample format), decoded on the device; "
                                  "not the headline e2e (its input is quantised to 16 bits)"},
+            "host_affinity_cpus": numa,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernel": {"grid": min(BATCH, info["sm_count"]), "block": info["threads_per_cta"],
