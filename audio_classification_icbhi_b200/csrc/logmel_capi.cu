@@ -29,7 +29,10 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 constexpr int kSlots = 3;   // host pipeline depth
-constexpr int kCounters = 64;   // launches of one plan that may be in flight at once (on any streams)
+constexpr int kCounters = 1024;      // launches of one plan that may be in flight at once (on any streams); a slot is
+                                     // re-zeroed on the launching stream right before its kernel, so launches on ONE
+                                     // stream never interfere, and 1024 concurrent streams per plan are out of reach
+constexpr int kMaxSplitClips = 512;  // small-batch mode is used below 2 * SM count clips
 
 struct HostSlot {
     cudaStream_t stream = nullptr;
@@ -65,7 +68,10 @@ struct lm_plan {
     HostSlot slots[kSlots];
     bool slots_ready = false;
     std::atomic<long long> launches{0};
-    int* d_counters = nullptr;   // kCounters work counters for the kernel's dynamic clip scheduling, one per launch in flight
+    int* d_counters = nullptr;   // kCounters x {work counter, finished groups} for the kernel's dynamic clip scheduling, one pair per launch in flight
+    // small-batch mode scratch, one block per launch in flight: [kMaxSplitClips][2] 64-bit sums, then [kMaxSplitClips] arrival counters
+    unsigned char* d_split = nullptr;
+    int split_override = 0;      // 0 = automatic, 1 = never split, k > 1 = at most k chunks per clip
 };
 
 namespace {
@@ -73,7 +79,7 @@ namespace {
 int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
-    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab); cudaFree(p->d_counters);
+    cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab); cudaFree(p->d_counters); cudaFree(p->d_split);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_pcm); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -107,10 +113,32 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     k.aug = aug; k.noise = noise; k.out_norm = out_norm; k.out_db = out_db; k.out_melpow = out_melpow;
     k.B = B; k.normalize = normalize;
     const long long seq = p->launches.fetch_add(1);
-    k.work_counter = p->d_counters + (seq % kCounters);
-    LM_CUDA(cudaMemsetAsync(k.work_counter, 0, sizeof(int), stream));
+    k.work_counter = p->d_counters + 2 * (seq % kCounters);   // zero now, left at zero by the kernel (no memset per launch)
     const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
-    const int grid = std::min<int>(B, cap);
+    // Small batches: fewer clips than 8-warp groups on the GPU.  Cut every clip into chunks of whole tiles so that
+    // (almost) every group gets one chunk; statistics are combined with integer atomics (logmel_kernel.cuh).
+    k.split = 1; k.tiles_per_chunk = p->n_tiles;
+    const int groups = cap * lm::kGroups;
+    if (normalize && p->split_override != 1 && B < groups && B <= kMaxSplitClips && p->n_tiles > 1) {
+        int want = groups / B;
+        if (p->split_override > 1) want = std::min(want, p->split_override);
+        want = std::max(1, std::min(want, p->n_tiles));
+        const int tpc = (p->n_tiles + want - 1) / want;
+        k.tiles_per_chunk = tpc;
+        k.split = (p->n_tiles + tpc - 1) / tpc;
+    }
+    if (!normalize && p->split_override != 1 && B < groups && p->n_tiles > 1) {   // nothing to combine: split freely
+        const int want = std::max(1, std::min(groups / B, p->n_tiles));
+        k.tiles_per_chunk = (p->n_tiles + want - 1) / want;
+        k.split = (p->n_tiles + k.tiles_per_chunk - 1) / k.tiles_per_chunk;
+    }
+    if (k.split > 1 && normalize) {
+        unsigned char* blk = p->d_split + static_cast<size_t>(seq % kCounters) * (kMaxSplitClips * 20);
+        k.clip_stats = reinterpret_cast<unsigned long long*>(blk);
+        k.clip_cnt = reinterpret_cast<int*>(blk + kMaxSplitClips * 16);
+        // zero at plan creation; the group that completes a clip resets its entries
+    }
+    const int grid = std::min<int>(B * k.split, cap);
     const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
     if (p->n_fft == 2048) {
         if (extra) lm::logmel_kernel<2048, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
@@ -150,7 +178,7 @@ const char* lm_strerror(int status) {
     switch (status) {
         case LM_OK: return "ok";
         case LM_ERR_INVALID_ARG: return "invalid argument";
-        case LM_ERR_UNSUPPORTED: return "unsupported configuration (n_fft must be 1024 or 2048; hop even and <= n_fft/4; n_mels <= 256)";
+        case LM_ERR_UNSUPPORTED: return "unsupported configuration (n_fft must be 1024 or 2048; hop even and <= n_fft/4; n_mels <= 256; window must be the periodic Hann window: w[n] + w[n + n_fft/2] = 1)";
         case LM_ERR_FILTERBANK: return "filterbank support too wide for the on-chip table";
         case LM_ERR_CUDA: return "CUDA runtime error (see lm_last_cuda_error)";
         case LM_ERR_NO_DEVICE: return "no usable CUDA device (an sm_100 GPU is required; there is no CPU fallback)";
@@ -169,6 +197,11 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
     if (cfg->n_mels < 1 || cfg->n_mels > 256) return LM_ERR_UNSUPPORTED;
     if (cfg->target_len <= cfg->n_fft / 2) return LM_ERR_TOO_SHORT;
     if (!(cfg->amin > 0.f)) return LM_ERR_INVALID_ARG;
+    // The kernel keeps half of the window and fuses it with the first butterfly through w[n + N/2] = 1 - w[n], which
+    // holds for the periodic Hann window of the reference (torch.hann_window, TA/transforms/_transforms.py:86-87) and
+    // for nothing else in common use: refuse other windows instead of computing wrong spectra.
+    for (int n = 0; n < cfg->n_fft / 2; ++n)
+        if (!(fabsf(cfg->window[n] + cfg->window[n + cfg->n_fft / 2] - 1.0f) <= 2e-6f)) return LM_ERR_UNSUPPORTED;
 
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
@@ -293,8 +326,11 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
         (rc = up(reinterpret_cast<void**>(&p->d_utw), utw.data(), sizeof(float2) * utw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_melw), melw.data(), sizeof(float4) * melw.size())) ||
         (rc = up(reinterpret_cast<void**>(&p->d_tab), &tab, sizeof(tab))) ||
-        (rc = (cudaMalloc(&p->d_counters, sizeof(int) * kCounters) == cudaSuccess &&
-               cudaMemset(p->d_counters, 0, sizeof(int) * kCounters) == cudaSuccess) ? LM_OK : cuda_fail(cudaGetLastError(), "work counters"))) {
+        (rc = (cudaMalloc(&p->d_counters, sizeof(int) * 2 * kCounters) == cudaSuccess &&
+               cudaMemset(p->d_counters, 0, sizeof(int) * 2 * kCounters) == cudaSuccess &&
+               cudaMalloc(&p->d_split, static_cast<size_t>(kCounters) * kMaxSplitClips * 20) == cudaSuccess &&
+               cudaMemset(p->d_split, 0, static_cast<size_t>(kCounters) * kMaxSplitClips * 20) == cudaSuccess)
+                  ? LM_OK : cuda_fail(cudaGetLastError(), "work counters"))) {
         free_plan(p);
         return rc;
     }
@@ -357,6 +393,7 @@ int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!strcmp(key, "host_chunk_clips")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->host_chunk_clips = value; return LM_OK; }
     if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
+    if (!strcmp(key, "split")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->split_override = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
 }
 

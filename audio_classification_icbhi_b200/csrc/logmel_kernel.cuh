@@ -34,6 +34,10 @@
 //           fp64 sum / sum-of-squares.
 //   silent  tiles that lie entirely in a plain clip's zero padding skip all of the above and write the floor /
 //           mask values and their statistics directly (bit-identical to the full path on a zero spectrum).
+//   split   small batches (B < number of groups on the GPU): a clip's tiles are dealt to `split` groups as
+//           "virtual clips" (clip, tile range); the per-clip statistics are 64-bit fixed-point sums (exact,
+//           order-independent integer adds), combined with atomics, and the group that arrives last
+//           normalises the whole clip.  Bit-identical to the unsplit path.
 //   norm    when the clip is finished the same group re-reads its (L2-resident) dB block and
 //           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116); for lm_forward_gather
 //           the same pass also stores the result into the other ranks' gathered buffers (multimem.st
@@ -119,9 +123,18 @@ struct KParams {
     int n_peer;
     float* mc_out;
     // dynamic clip scheduling: clips [0, 2*gridDim) are dealt statically (one per group); every further clip
-    // is fetched with atomicAdd on this counter (zeroed by the host before the launch) when a group starts the
-    // last tile of its current clip, so that ragged batches (unequal numbers of silent tiles) stay balanced
+    // is fetched with atomicAdd on work_counter[0] when a group starts the last tile of its current clip, so that
+    // ragged batches (unequal numbers of silent tiles) stay balanced.  work_counter[1] counts the groups that have
+    // finished; the last one puts both back to zero, so a launch needs no memset (the counters start at zero when
+    // the plan is created and every launch leaves them at zero).
     int* work_counter;
+    // small-batch mode: every clip is cut into `split` chunks of `tiles_per_chunk` tiles (the last one may be
+    // shorter, none is empty); virtual clip v = clip * split + chunk.  clip_stats[2 clip .. 2 clip + 1] and
+    // clip_cnt[clip] are zero before the launch and put back to zero by the group that completes the clip
+    // (used only when split > 1).
+    int split, tiles_per_chunk;
+    unsigned long long* clip_stats;
+    int* clip_cnt;
     // plan
     int T, hop, frames, n_mels, n_tiles;
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
@@ -207,6 +220,17 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 }
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+
+// Per-clip statistics are exact integers: a thread's fp32 partial sums of one item are rounded once to
+// 2^-24 (sum) / 2^-16 (sum of squares) and added as 64-bit integers, so the totals do not depend on which
+// group processed which tile, nor on the order of the additions (small-batch mode relies on this).
+constexpr float kStatScaleS = 16777216.0f, kStatScaleQ = 65536.0f;
+__device__ __forceinline__ void stat_add(longlong2* __restrict__ slot, float ssum, float qsum) {
+    longlong2 st = *slot;
+    st.x += __float2ll_rn(ssum * kStatScaleS);
+    st.y += __float2ll_rn(qsum * kStatScaleQ);
+    *slot = st;
+}
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 -> N(0,1): throughput-mode noise when no host-drawn noise is supplied
@@ -319,11 +343,11 @@ struct Geo {
 template <int NFFT>
 struct Smem {
     static constexpr size_t kBar = 0;                                    // kGroups mbarriers + 'TMA pending' flags
-    static constexpr size_t kRed = kBar + 32;                            // per group: reduction scratch + broadcast
-    static constexpr size_t kRedGroup = sizeof(double) * 2 * kGroupWarps + 16;
+    static constexpr size_t kRed = kBar + 48;                            // + the filterbank-copy mbarrier at +32                            // per group: reduction scratch + broadcast
+    static constexpr size_t kRedGroup = sizeof(long long) * 2 * kGroupWarps + 16;   // + bcast[3]: mean, std + eps, 'this group normalises'
     static constexpr size_t kCtx = kRed + kGroups * kRedGroup;           // per group two ClipCtx slots (ordinal & 1)
     static constexpr size_t kTab = kCtx + kGroups * 2 * 80;
-    static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fp64 (sum, sumsq)
+    static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fixed-point (sum, sumsq)
     static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
     static constexpr size_t kTw = kWin + sizeof(float) * (NFFT / 2);     // first half of the window
     static constexpr size_t kUtw = kTw + sizeof(float2) * 32 * kTwRows;
@@ -349,12 +373,15 @@ struct alignas(16) ClipCtx {
     int plain;
     int silent_from;     // first tile that lies entirely in the zero padding (n_tiles if none); plain clips only
     int clip;            // index of the clip in the batch; -1 in the "next clip" slot = the batch is exhausted
-    int pad_;
+    int t_begin, t_end;  // tile range of this virtual clip
 };
 constexpr int kCtxSlot = 80;
 static_assert(sizeof(ClipCtx) <= kCtxSlot && kCtxSlot % 16 == 0, "ClipCtx slot size");
 
-__device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* __restrict__ c, int nfft) {
+__device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* __restrict__ c, int nfft) {
+    const int clip = vclip / p.split, chunk = vclip - clip * p.split;
+    c->t_begin = chunk * p.tiles_per_chunk;
+    c->t_end = (c->t_begin + p.tiles_per_chunk < p.n_tiles) ? c->t_begin + p.tiles_per_chunk : p.n_tiles;
     const long long off = p.offset[clip];
     const int len = p.length[clip];
     const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
@@ -366,7 +393,8 @@ __device__ __forceinline__ void load_clip(const KParams& p, int clip, ClipCtx* _
     uint64_t seed = 0;
     if (p.aug != nullptr) {
         const lm_aug a = p.aug[clip];
-        shift = a.shift; nscale = a.noise_scale; gain = a.gain;
+        shift = a.shift % p.T;   // torch.roll takes any shift; the staging wraps once
+        nscale = a.noise_scale; gain = a.gain;
         f0 = a.f0; f1 = a.f1; t0 = a.t0; t1 = a.t1; seed = a.seed;
     }
     c->shift = shift; c->f0 = f0; c->f1 = f1; c->t0 = t0; c->t1 = t1;
@@ -406,11 +434,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + L::kBar) + group;
     volatile int* const s_pend = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 16) + group;
-    double* const red = reinterpret_cast<double*>(smem_raw + L::kRed + group * L::kRedGroup);
-    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + group * L::kRedGroup + sizeof(double) * 2 * kGroupWarps);
+    long long* const red = reinterpret_cast<long long*>(smem_raw + L::kRed + group * L::kRedGroup);
+    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + group * L::kRedGroup + sizeof(long long) * 2 * kGroupWarps);
     ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx) + 2 * group;
     const MelTable* const s_tab = reinterpret_cast<const MelTable*>(smem_raw + L::kTab);
-    double2* const s_stat = reinterpret_cast<double2*>(smem_raw + L::kStat);
+    longlong2* const s_stat = reinterpret_cast<longlong2*>(smem_raw + L::kStat);
     float* const s_win = reinterpret_cast<float*>(smem_raw + L::kWin);
     float2* const s_tw = reinterpret_cast<float2*>(smem_raw + L::kTw);
     float2* const s_utw = reinterpret_cast<float2*>(smem_raw + L::kUtw);
@@ -423,7 +451,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     for (int i = tid; i < 32 * kTwRows; i += kThreads) s_tw[i] = p.tw[i];
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
-    for (int i = tid; i < 64 * p.n_dk; i += kThreads) s_melw[i] = p.melw[i];
+    // the banded filterbank (up to 96 KB) is needed first in the mel phase of the first item: one bulk copy, in flight
+    // during the first FFT, completing on its own mbarrier (every thread waits for it once, before its first mel phase)
+    uint64_t* const mbar_fb = reinterpret_cast<uint64_t*>(smem_raw + L::kBar + 32);
+    if (tid == 0) {
+        mbar_init(mbar_fb, 1);
+        fence_mbar_init();
+        mbar_expect_tx(mbar_fb, static_cast<uint32_t>(p.n_dk) * 1024u);
+        bulk_g2s(s_melw, p.melw, static_cast<uint32_t>(p.n_dk) * 1024u, mbar_fb);
+    }
     for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
         reinterpret_cast<int*>(smem_raw + L::kTab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
     for (int i = gtid; i < kGroupWarps * kRowFloats; i += kGroupThreads) rows[i] = 0.0f;   // pad columns stay finite
@@ -437,8 +473,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 
     // ---- this group's clips -----------------------------------------------------------------------
     const int nv = static_cast<int>(gridDim.x) * kGroups;
-    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);   // first clip: static
-    if (clip0 >= p.B) return;
+    const int n_virtual = p.B * p.split;
+    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);   // first (virtual) clip: static
+    if (clip0 >= n_virtual) return;
 
     const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
     const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
@@ -512,10 +549,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     // ---- prologue: item 0 is staged before the loop; item it+1 is staged during item it ----------------
     if (gtid == 0) {
         load_clip(p, clip0, &s_ctx[0], NFFT);
-        stage_bulk(&s_ctx[0], 0);
+        stage_bulk(&s_ctx[0], s_ctx[0].t_begin);
     }
     group_bar(group);
-    stage_gather(&s_ctx[0], 0);
+    stage_gather(&s_ctx[0], s_ctx[0].t_begin);
     group_bar(group);
     if (group == 1 && p.stagger_ns > 0) {   // spin (nanosleep may return early): ~2 cycles per ns
         const long long t_end = clock64() + 2LL * p.stagger_ns;
@@ -523,8 +560,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     }
 
     uint32_t parity = 0;                   // mbarrier phase of the staging buffer (group-uniform)
-    s_stat[tid] = make_double2(0.0, 0.0);  // this thread's running (sum, sum of squares) of the clip's dB values
-    int tile = 0, ord = 0, clip = clip0;   // tile index, clip ordinal (context slot = ord & 1) and clip index of the item
+    bool fb_ready = false;                 // this thread has seen the filterbank copy complete
+    s_stat[tid] = make_longlong2(0, 0);    // this thread's running (sum, sum of squares) of the clip's dB values, fixed point
+    int tile = s_ctx[0].t_begin, t_end = s_ctx[0].t_end, ord = 0, clip = s_ctx[0].clip;   // tile, end of the tile range, clip ordinal (context slot = ord & 1), clip index
 
 #if LM_TIMING
     long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -544,16 +582,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
         // item it+1: its TMA part goes into the buffer consumed by (A); one thread; the clip's context slot is
         // filled when its first tile comes up
-        int tile1 = tile + 1, ord1 = ord;
-        if (tile1 == p.n_tiles) { tile1 = 0; ++ord1; }
+        const bool wrap = (tile + 1 == t_end);   // last tile of this (virtual) clip
+        int tile1 = tile + 1, ord1 = ord;        // tile1 of a new clip is its t_begin: read from the context after barrier (B)
+        if (wrap) ++ord1;
         auto issue_next = [&]() {
             if (gtid == 0) {
                 ClipCtx* const cn = &s_ctx[ord1 & 1];
-                if (tile1 == 0) {   // last tile of this clip: fetch the group's next clip
+                if (wrap) {   // fetch the group's next (virtual) clip
                     const int nxt = nv + atomicAdd(p.work_counter, 1);
-                    if (nxt < p.B) {
+                    if (nxt < n_virtual) {
                         load_clip(p, nxt, cn, NFFT);
-                        stage_bulk(cn, 0);
+                        stage_bulk(cn, cn->t_begin);
                     } else {
                         cn->clip = -1;
                     }
@@ -588,10 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     qsum = fmaf(v, v, qsum);
                 }
             }
-            double2 st = s_stat[tid];
-            st.x += static_cast<double>(ssum);
-            st.y += static_cast<double>(qsum);
-            s_stat[tid] = st;
+            stat_add(&s_stat[tid], ssum, qsum);
         } else {
         lm_f2 z[32];
         if (LM_EXP != 2) {
@@ -713,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         LM_T(4);   // barrier B
 
         // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
+        if (!fb_ready) { mbar_wait(mbar_fb, 0); fb_ready = true; }
         {
             const int lane = launder(lane_), gw = launder(gwarp_);
             const int g = lane >> 2, tg = lane & 3;
@@ -786,26 +823,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     qsum = fmaf(u0, u0, fmaf(u1, u1, qsum));
                 }
             }
-            double2 st = s_stat[tid];
-            st.x += static_cast<double>(ssum);
-            st.y += static_cast<double>(qsum);
-            s_stat[tid] = st;
+            stat_add(&s_stat[tid], ssum, qsum);
         }
 
         }   // not silent
         LM_T(5);   // mel phase
         // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
-        const bool has1 = (tile1 != 0) || (s_ctx[ord1 & 1].clip >= 0);   // written before (B) by thread 0
+        const bool has1 = !wrap || (s_ctx[ord1 & 1].clip >= 0);   // written before (B) by thread 0
+        if (wrap && has1) tile1 = s_ctx[ord1 & 1].t_begin;
         if (has1) {
             if (stage_gather(&s_ctx[ord1 & 1], tile1)) group_bar(group);   // (C) only for tiles that touch a clip edge
         }
 
         LM_T(6);   // gather + barrier C
         // ---- per-clip normalisation --------------------------------------------------------------------
-        if (tile + 1 == p.n_tiles) {
+        if (wrap) {
             if (p.normalize) {
                 float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
-                double s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
+                long long s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
@@ -814,16 +849,37 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 if (lane_ == 0) { red[gwarp_] = s_acc; red[kGroupWarps + gwarp_] = q_acc; }
                 group_bar(group);   // also orders every thread's dB stores before the re-read below
                 if (gtid == 0) {
-                    double s = 0.0, q = 0.0;
-                    for (int w = 0; w < kGroupWarps; ++w) { s += red[w]; q += red[kGroupWarps + w]; }
+                    long long si = 0, qi = 0;
+                    for (int w = 0; w < kGroupWarps; ++w) { si += red[w]; qi += red[kGroupWarps + w]; }
+                    bool last = true;
+                    if (p.split > 1) {
+                        // this chunk's sums join the clip's; the group whose arrival completes the clip normalises it.
+                        // The fence makes the group's dB stores (ordered before it by the barrier above) visible GPU-wide
+                        // before the arrival counter moves.
+                        atomicAdd(p.clip_stats + 2 * clip, static_cast<unsigned long long>(si));
+                        atomicAdd(p.clip_stats + 2 * clip + 1, static_cast<unsigned long long>(qi));
+                        __threadfence();
+                        last = atomicAdd(p.clip_cnt + clip, 1) == p.split - 1;
+                        if (last) {
+                            __threadfence();
+                            si = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip));
+                            qi = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip + 1));
+                            p.clip_stats[2 * clip] = 0ull;       // nobody else touches this clip's scratch any more
+                            p.clip_stats[2 * clip + 1] = 0ull;
+                            p.clip_cnt[clip] = 0;
+                        }
+                    }
+                    const double s = static_cast<double>(si) * (1.0 / kStatScaleS), q = static_cast<double>(qi) * (1.0 / kStatScaleQ);
                     const double n = static_cast<double>(clip_elems);
                     const double mean = s / n;
                     double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
                     if (!(var > 0.0)) var = 0.0;
                     bcast[0] = static_cast<float>(mean);
                     bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
+                    bcast[2] = last ? 1.0f : 0.0f;
                 }
                 group_bar(group);
+                if (bcast[2] != 0.0f) {
                 const float mean = bcast[0], inv = 1.0f / bcast[1];
                 float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
                 const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
@@ -855,16 +911,29 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 }
                 for (int i = (n4 << 2) + gtid; i < static_cast<int>(clip_elems); i += kGroupThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;
+                }   // this group finishes the clip
+                group_bar(group);   // bcast is rewritten at the next clip end
             }
             if (!has1) break;
-            s_stat[tid] = make_double2(0.0, 0.0);
+            s_stat[tid] = make_longlong2(0, 0);
             clip = s_ctx[ord1 & 1].clip;
-            tile = 0;
+            tile = tile1;
+            t_end = s_ctx[ord1 & 1].t_end;
             ++ord;
         } else {
             ++tile;
         }
         LM_T(7);   // normalisation
+    }
+    if (!fb_ready) mbar_wait(mbar_fb, 0);   // (all tiles silent) never leave a bulk copy in flight behind an exiting CTA
+    // the last group to finish leaves the launch's counters at zero for the next launch that uses this slot
+    if (gtid == 0) {
+        const int active = n_virtual < nv ? n_virtual : nv;
+        __threadfence();
+        if (atomicAdd(p.work_counter + 1, 1) == active - 1) {
+            p.work_counter[0] = 0;
+            p.work_counter[1] = 0;
+        }
     }
 #if LM_TIMING
     if (lane_ == 0) {

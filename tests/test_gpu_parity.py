@@ -429,3 +429,40 @@ def test_forward_is_cuda_graph_capturable(A):
     eager = plan.forward(clips.view(-1), offset, length)
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_small_batch_split_is_bit_identical(A):
+    """Small batches cut every clip into tile ranges handled by different groups; the
+    statistics are exact integer sums, so the features equal the one-group-per-clip path bit for bit --
+    ragged clips, silent tiles, masks and the un-normalised outputs included."""
+    plan = get_plan(A)
+    rs = np.random.RandomState(21)
+    T = plan.target_length
+    for lens in ([T], [T, 30000, T + 777], [int(rs.randint(2000, 2 * T)) for _ in range(32)]):
+        clips = [(rs.standard_normal(n) * 0.1).astype(np.float32) for n in lens]
+        aug = A.plan.make_aug_array(len(clips))
+        aug["f0"], aug["f1"], aug["t0"], aug["t1"] = 10, 17, 100, 131
+        aug["shift"][::2] = 1234
+        aug["shift"][1::2] = -3 * T - 17      # any shift is legal for torch.roll
+        plan.set("split", 1)
+        ref = run_clips(plan, clips, aug=aug)
+        plan.set("split", 0)
+        got = run_clips(plan, clips, aug=aug)
+        for key in ("out", "db", "mel_power"):
+            np.testing.assert_array_equal(got[key], ref[key])
+        plan.set("split", 3)
+        got3 = run_clips(plan, clips, aug=aug, want_stages=False)
+        plan.set("split", 0)
+        np.testing.assert_array_equal(got3["out"], ref["out"])
+    # the roll wraps: a shift of -3T - 17 is a shift of -17
+    x = (rs.standard_normal(T) * 0.1).astype(np.float32)
+    a1, a2 = A.plan.make_aug_array(1), A.plan.make_aug_array(1)
+    a1["shift"], a2["shift"] = -3 * T - 17, -17
+    np.testing.assert_array_equal(run_clips(plan, [x], aug=a1)["out"], run_clips(plan, [x], aug=a2)["out"])
+
+
+def test_non_hann_window_is_refused(A):
+    """The kernel relies on w[n + N/2] = 1 - w[n] (periodic Hann): any other window must fail at plan creation."""
+    with pytest.raises(RuntimeError, match="unsupported"):
+        A.LogMelPlan(window=torch.hamming_window(2048), device="cuda:0")
+    A.LogMelPlan(window=torch.hann_window(2048), device="cuda:0").close()
