@@ -9,7 +9,7 @@ shims under the reference's own module paths.
 from .plan import LogMelPlan, make_aug_array, reference_filterbank, reference_window
 from .preprocessing import AudioPreprocessor
 from .preprocessing_flexible import FlexibleAudioPreprocessor
-from .dataset import GpuCollate, ICBHIDataset, ICBHISegmentedDataset
+from .dataset import GpuCollate, GpuLoader, ICBHIDataset, ICBHISegmentedDataset, raw_collate
 from .analyzer import SlidingWindowLogMel, segment_offsets
 from .segmenter import ICBHISegmenter
 from .sharding import FusedGather, ShardedLogMel, shard_bounds, shard_size
@@ -19,7 +19,7 @@ from .resample import Resampler, get_resampler
 __all__ = [
     "LogMelPlan", "make_aug_array", "reference_filterbank", "reference_window",
     "AudioPreprocessor", "FlexibleAudioPreprocessor",
-    "ICBHIDataset", "ICBHISegmentedDataset", "GpuCollate",
+    "ICBHIDataset", "ICBHISegmentedDataset", "GpuCollate", "GpuLoader", "raw_collate",
     "SlidingWindowLogMel", "segment_offsets", "ICBHISegmenter",
     "ShardedLogMel", "FusedGather", "shard_bounds", "shard_size",
     "draw_fast_augmentation", "draw_reference_augmentation",

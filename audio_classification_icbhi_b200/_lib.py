@@ -64,6 +64,7 @@ EXPORTS = {
     "lm_forward_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "lm_pcm16_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "lm_amplitude_to_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "lm_resampler_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
     "lm_resampler_destroy": (C.c_int, [C.c_void_p]),
     "lm_resampler_out_len": (C.c_int64, [C.c_void_p, C.c_int64]),

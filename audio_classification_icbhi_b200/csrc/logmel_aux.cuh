@@ -85,6 +85,15 @@ __global__ void pcm16_roundtrip_kernel(const float* __restrict__ in, float* __re
     }
 }
 
+// T.AmplitudeToDB() on its own (R/src/data/preprocessing.py:46, TA/functional/functional.py:390-391):
+// y = multiplier * log10(max(x, amin)) - offset, element-wise; the drop-in preprocessor's `amplitude_to_db` attribute.
+__global__ void amplitude_to_db_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float db_scale, float amin,
+                                       float db_offset) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fmaf(db_scale, log2f(fmaxf(in[i], amin)), -db_offset);
+}
+
 // 16-bit PCM -> fp32: x / 32768 (exact), what torchaudio.load(normalize=True) hands the reference for a
 // PCM_16 wav (R/src/data/preprocessing.py:57).  Eight samples per thread per pass: one 128-bit load, two
 // 128-bit stores; `in` and `out` must be 16-byte aligned, the tail is done element-wise.

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -27,6 +28,20 @@ int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t _e = (call);                             \
         if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
     } while (0)
+
+// The companion entry points take raw device pointers and a stream but no plan: make the device that owns the
+// pointer current for the launch (a caller on cuda:0 may hold tensors of cuda:1) and restore it afterwards.
+struct DeviceOf {
+    int prev = -1, dev = -1;
+    explicit DeviceOf(const void* ptr) {
+        cudaPointerAttributes a{};
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (ptr && cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) dev = a.device;
+        cudaGetLastError();
+        if (dev >= 0 && dev != prev) cudaSetDevice(dev); else dev = -1;
+    }
+    ~DeviceOf() { if (dev >= 0 && prev >= 0) cudaSetDevice(prev); }
+};
 
 constexpr int kSlots = 3;   // host pipeline depth
 constexpr int kCounters = 1024;      // launches of one plan that may be in flight at once (on any streams); a slot is
@@ -72,6 +87,7 @@ struct lm_plan {
     // small-batch mode scratch, one block per launch in flight: [kMaxSplitClips][2] 64-bit sums, then [kMaxSplitClips] arrival counters
     unsigned char* d_split = nullptr;
     int split_override = 0;      // 0 = automatic, 1 = never split, k > 1 = at most k chunks per clip
+    std::mutex host_mu;          // lm_forward_host*: one caller at a time per plan (plan-owned staging buffers)
 };
 
 namespace {
@@ -439,6 +455,7 @@ int lm_resize_finish(const float* in, int32_t B, int32_t n_mels, int32_t frames_
     if (B < 0 || n_mels < 1 || frames_in < 1 || frames_out < 1) return LM_ERR_INVALID_ARG;
     if (B == 0) return LM_OK;
     if (!in || !out || in == out) return LM_ERR_INVALID_ARG;
+    DeviceOf guard(out);
     lm::resize_finish_kernel<<<B, lm::kAuxThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
         in, out, aug, n_mels, frames_in, frames_out, normalize, norm_eps);
     LM_CUDA(cudaGetLastError());
@@ -449,6 +466,7 @@ int lm_pcm16_roundtrip(const float* in, float* out, int64_t n, void* cuda_stream
     if (n < 0) return LM_ERR_INVALID_ARG;
     if (n == 0) return LM_OK;
     if (!in || !out) return LM_ERR_INVALID_ARG;
+    DeviceOf guard(out);
     const int blocks = static_cast<int>(std::min<int64_t>((n + 1023) / 1024, 148 * 8));
     lm::pcm16_roundtrip_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, out, n);
     LM_CUDA(cudaGetLastError());
@@ -544,6 +562,7 @@ int lm_resample_rows(const lm_resampler* r, const float* in, int64_t in_len, int
     const int64_t n_out = lm_resampler_out_len(r, in_len);
     if (n_out == 0 || n_rows == 0) return LM_OK;
     if (!in || !out || in_stride < in_len || out_stride < n_out) return LM_ERR_INVALID_ARG;
+    DeviceOf guard(out);
     const int threads = 256;
     const long long blocks = (n_out + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return LM_ERR_INVALID_ARG;
@@ -562,10 +581,23 @@ int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* o
     return lm_resample_rows(r, in, in_len, in_len, 1, out, lm_resampler_out_len(r, in_len), cuda_stream);
 }
 
+int lm_amplitude_to_db(const float* in, float* out, int64_t n, float multiplier, float amin, float db_offset, void* cuda_stream) {
+    if (n < 0 || !(amin > 0.f)) return LM_ERR_INVALID_ARG;
+    if (n == 0) return LM_OK;
+    if (!in || !out) return LM_ERR_INVALID_ARG;
+    DeviceOf guard(out);
+    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+    lm::amplitude_to_db_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        in, out, n, static_cast<float>(static_cast<double>(multiplier) * 0.30102999566398119521), amin, db_offset);
+    LM_CUDA(cudaGetLastError());
+    return LM_OK;
+}
+
 int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream) {
     if (n < 0) return LM_ERR_INVALID_ARG;
     if (n == 0) return LM_OK;
     if (!in || !out || (reinterpret_cast<uintptr_t>(in) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return LM_ERR_INVALID_ARG;
+    DeviceOf guard(out);
     const int blocks = static_cast<int>(std::min<int64_t>((n / 8 + 255) / 256 + 1, 148 * 8));
     lm::pcm16_decode_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, out, n);
     LM_CUDA(cudaGetLastError());
@@ -598,6 +630,7 @@ static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, in
     if (!wave || !offset || !length || !out) return LM_ERR_INVALID_ARG;
     for (int i = 0; i < B; ++i)
         if (length[i] < 0 || offset[i] < 0 || offset[i] + length[i] > total_samples) return LM_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> one_caller(plan->host_mu);   // the staging slots belong to the plan
     int dev = -1;
     LM_CUDA(cudaGetDevice(&dev));
     LM_CUDA(cudaSetDevice(plan->device));

@@ -18,7 +18,7 @@ from torch.utils.data import Dataset
 
 from .preprocessing import AudioPreprocessor
 
-__all__ = ["ICBHIDataset", "ICBHISegmentedDataset", "GpuCollate"]
+__all__ = ["ICBHIDataset", "ICBHISegmentedDataset", "GpuCollate", "GpuLoader", "raw_collate"]
 
 
 def _build_preprocessor(config, augment: bool) -> AudioPreprocessor:
@@ -32,11 +32,13 @@ def _build_preprocessor(config, augment: bool) -> AudioPreprocessor:
 class _RawMixin:
     """Raw mode shared by both datasets."""
 
-    def raw_item(self, idx) -> Tuple[torch.Tensor, int]:
-        """(waveform `[1, len]` float32 mono at the target rate, label): no feature extraction,
-        safe inside forked workers."""
+    def raw_item(self, idx) -> Tuple[torch.Tensor, int, int]:
+        """(waveform `[1, len]` float32 mono at the FILE's sample rate, that rate, label): decode only.  No CUDA call
+        -- raw ICBHI recordings are 4 / 10 / 44.1 kHz and resampling runs on the GPU, which a forked DataLoader
+        worker must not touch; `GpuCollate` resamples in the process that owns the context."""
         audio_path, label = self.data[idx]
-        return self.preprocessor.load_audio(audio_path), label
+        waveform, sr = self.preprocessor.decode_audio(audio_path)
+        return waveform, sr, label
 
     def raw(self) -> "RawView":
         """A Dataset view whose items are `raw_item`s (for DataLoader + GpuCollate)."""
@@ -62,18 +64,56 @@ class RawView(Dataset):
 
 
 class GpuCollate:
-    """collate_fn for raw items: list of (waveform, label) -> (features [B,1,n_mels,frames] on the
-    GPU, labels int64 on the GPU).  Call it in the process that owns the CUDA context."""
+    """collate_fn for raw items: list of (waveform, sample_rate, label) -- or (waveform, label) for waveforms already
+    at the target rate -- -> (features [B,1,n_mels,frames] on the GPU, labels int64 on the GPU).  Recordings at
+    another rate are resampled here, on the GPU (`lm_resample`), then the whole batch is ONE `lm_forward` launch.
+    It must run in the process that owns the CUDA context.  A DataLoader calls its collate_fn INSIDE the worker
+    processes, so with `num_workers > 0` give the loader `raw_collate` (workers hand back plain lists) and wrap it in
+    `GpuLoader(loader, GpuCollate(...))`, which collates in the training process; with `num_workers=0` it can be
+    the collate_fn itself."""
 
     def __init__(self, preprocessor: AudioPreprocessor, fast_augment: bool = False):
         self.preprocessor = preprocessor
         self.fast_augment = fast_augment
 
-    def __call__(self, batch: Sequence[Tuple[torch.Tensor, int]]):
-        waves = [w for w, _ in batch]
-        labels = torch.tensor([int(y) for _, y in batch], dtype=torch.int64)
+    def __call__(self, batch: Sequence[tuple]):
+        waves, labels = [], []
+        for item in batch:
+            if len(item) == 3:
+                w, sr, y = item
+                w = self.preprocessor.resample_to_target(w, sr)
+            else:
+                w, y = item
+            waves.append(w)
+            labels.append(int(y))
         feats = self.preprocessor.preprocess_batch(waves, fast_augment=self.fast_augment)
-        return feats, labels.to(feats.device, non_blocking=True)
+        return feats, torch.tensor(labels, dtype=torch.int64).to(feats.device, non_blocking=True)
+
+
+def raw_collate(batch):
+    """collate_fn for `DataLoader(dataset.raw(), num_workers > 0)`: keep the list of raw items as it is (decoded
+    waveforms of different lengths and rates cannot be stacked, and the workers must not touch CUDA)."""
+    return list(batch)
+
+
+class GpuLoader:
+    """Iterates a DataLoader of raw batches and turns each into (features, labels) on the GPU in THIS process:
+
+        loader = DataLoader(ds.raw(), batch_size=32, shuffle=True, num_workers=4, collate_fn=raw_collate)
+        for inputs, labels in GpuLoader(loader, GpuCollate(ds.preprocessor)): ...
+
+    replaces R/src/training/trainer_fixed.py:35-50 + :146-147 (the workers decode, one kernel launch per batch
+    extracts the features, `inputs.to(device)` becomes a no-op)."""
+
+    def __init__(self, loader, collate: GpuCollate):
+        self.loader, self.collate = loader, collate
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for raw in self.loader:
+            yield self.collate(raw)
 
 
 class ICBHIDataset(_RawMixin, Dataset):

@@ -36,6 +36,68 @@ def _as_mono_1d(w: Wave) -> torch.Tensor:
     return t.to(torch.float32)
 
 
+class _DeviceTransform:
+    """Base of the callable attributes the reference class exposes (`mel_spectrogram`, `amplitude_to_db`,
+    `freq_mask`, `time_mask`: R/src/data/preprocessing.py:38-53).  Tensors go to the GPU and come back on the
+    device they arrived on, so a caller that treats them like the torchaudio transforms keeps working."""
+
+    def __init__(self, owner: "AudioPreprocessor"):
+        self._owner = owner
+
+
+class _MelSpectrogram(_DeviceTransform):
+    """`T.MelSpectrogram(sample_rate, n_fft, hop_length, n_mels, power=2.0)` (preprocessing.py:38-44): `[..., len]`
+    -> `[..., n_mels, 1 + len // hop]` mel power.  One launch of the fused kernel with `out_melpow` and no
+    normalisation; plans are cached per waveform length."""
+
+    def __call__(self, waveform: torch.Tensor) -> torch.Tensor:
+        o = self._owner
+        w = torch.as_tensor(waveform, dtype=torch.float32)
+        lead, n = w.shape[:-1], int(w.shape[-1])
+        plan = o._plan_for_length(n)
+        rows = w.reshape(-1, n).to(plan.device).contiguous()
+        B = rows.shape[0]
+        melp = torch.empty(plan.out_shape(B), dtype=torch.float32, device=plan.device)
+        scratch = torch.empty_like(melp)
+        plan.forward_dense(rows, normalize=False, out=scratch, out_melpow=melp)
+        return melp.reshape(*lead, o.n_mels, plan.frames).to(w.device)
+
+
+class _AmplitudeToDB(_DeviceTransform):
+    """`T.AmplitudeToDB()` (preprocessing.py:46): 10 log10(max(x, 1e-10)), no top_db."""
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        import ctypes as C
+        o = self._owner
+        src = torch.as_tensor(x, dtype=torch.float32)
+        dev = o.plan.device
+        d = src.to(dev).contiguous()
+        out = torch.empty_like(d)
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev)
+            _lib.check(_lib.load().lm_amplitude_to_db(d.data_ptr(), out.data_ptr(), d.numel(), 10.0, 1e-10, 0.0,
+                                                      C.c_void_p(s.cuda_stream)))
+        return out.to(src.device)
+
+
+class _AxisMask(_DeviceTransform):
+    """`T.FrequencyMasking(15)` / `T.TimeMasking(35)` (preprocessing.py:52-53): one interval per call, drawn from torch's
+    global generator exactly as torchaudio.functional.mask_along_axis draws it, filled with 0.0."""
+
+    def __init__(self, owner, mask_param: int, axis: int):
+        super().__init__(owner)
+        self.mask_param, self.axis = mask_param, axis
+
+    def __call__(self, spec: torch.Tensor, mask_value: float = 0.0) -> torch.Tensor:
+        from .augment import mask_interval
+        a, b = mask_interval(self.mask_param, spec.shape[self.axis])
+        out = spec.clone()
+        a = max(a, 0)
+        if b > a:
+            out.narrow(self.axis, a, min(b, spec.shape[self.axis]) - a).fill_(mask_value)
+        return out
+
+
 class AudioPreprocessor:
     """Audio preprocessing for respiratory sounds: resampling, log-mel, normalisation, augmentation."""
 
@@ -54,7 +116,15 @@ class AudioPreprocessor:
         self.target_length = int(sample_rate * duration)
         self._device = device
         self._plan: Optional[LogMelPlan] = None
+        self._length_plans = {}
         _lib.load()   # fail loudly at construction if the CUDA library is not built
+        # the transform objects of the reference class (preprocessing.py:38-53), GPU-backed
+        self.mel_spectrogram = _MelSpectrogram(self)
+        self.amplitude_to_db = _AmplitudeToDB(self)
+        if augment:
+            self.time_stretch = None          # T.TimeStretch is constructed by the reference but never called
+            self.freq_mask = _AxisMask(self, self.freq_mask_param, -2)
+            self.time_mask = _AxisMask(self, self.time_mask_param, -1)
 
     # -- plan -------------------------------------------------------------------------------
     @property
@@ -66,6 +136,17 @@ class AudioPreprocessor:
                                     n_mels=self.n_mels, target_length=self.target_length, device=self._device)
         return self._plan
 
+    def _plan_for_length(self, n: int) -> LogMelPlan:
+        """Plan whose target length is the waveform's own length (the transform attributes neither pad nor crop)."""
+        if n == self.target_length:
+            return self.plan
+        if n not in self._length_plans:
+            if len(self._length_plans) >= 8:
+                self._length_plans.pop(next(iter(self._length_plans))).close()
+            self._length_plans[n] = LogMelPlan(sample_rate=self.sample_rate, n_fft=self.n_fft, hop_length=self.hop_length,
+                                               n_mels=self.n_mels, target_length=n, device=self._device)
+        return self._length_plans[n]
+
     @property
     def stft_frames(self) -> int:
         return 1 + self.target_length // self.hop_length
@@ -76,8 +157,10 @@ class AudioPreprocessor:
         return self.stft_frames
 
     # -- reference helper methods (host-side glue, same semantics) ---------------------------------
-    def load_audio(self, audio_path):
-        """File -> `[1, len]` float32 mono at `sample_rate` (preprocessing.py:55-68)."""
+    def decode_audio(self, audio_path):
+        """File -> (`[1, len]` float32 mono at the FILE's rate, sample_rate).  Host only -- never touches CUDA, so it
+        is what forked DataLoader workers call (raw mode); resampling to `sample_rate` happens on the GPU in the
+        process that owns the context (`load_audio`, `GpuCollate`)."""
         try:
             import torchaudio
             waveform, sr = torchaudio.load(audio_path)
@@ -86,11 +169,20 @@ class AudioPreprocessor:
             waveform = torch.from_numpy(data)
         if waveform.shape[0] > 1:
             waveform = torch.mean(waveform, dim=0, keepdim=True)
-        if sr != self.sample_rate:
-            # T.Resample(sr, self.sample_rate) of the reference (preprocessing.py:63-65), as a CUDA kernel
-            from .resample import get_resampler
-            waveform = get_resampler(int(sr), int(self.sample_rate), self.plan.device)(waveform.float()).cpu()
-        return waveform
+        return waveform.to(torch.float32), int(sr)
+
+    def resample_to_target(self, waveform, sr):
+        """`T.Resample(sr, self.sample_rate)` of the reference (preprocessing.py:63-65) as a CUDA kernel; returns a
+        device tensor when it resamples, the input unchanged when the rates agree."""
+        if int(sr) == int(self.sample_rate):
+            return waveform
+        from .resample import get_resampler
+        return get_resampler(int(sr), int(self.sample_rate), self.plan.device)(waveform.float())
+
+    def load_audio(self, audio_path):
+        """File -> `[1, len]` float32 mono at `sample_rate` (preprocessing.py:55-68)."""
+        waveform, sr = self.decode_audio(audio_path)
+        return self.resample_to_target(waveform, sr).cpu()
 
     def pad_or_crop(self, waveform):
         """Right zero-pad or centre-crop to `target_length` (preprocessing.py:70-83)."""

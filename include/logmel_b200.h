@@ -27,11 +27,15 @@
  * Conventions
  *   - every function returns LM_OK (0) or a negative lm_status; nothing throws across the ABI.
  *   - lm_forward allocates nothing, enqueues on the caller's stream and does not synchronise.
- *   - a plan's tables are immutable after creation: concurrent lm_forward calls on different streams
- *     are safe (each launch takes one of 64 plan-owned work counters, zeroed on the caller's stream
- *     right before the kernel: keep fewer than 64 launches of one plan in flight; a launch captured
- *     in a CUDA graph keeps its counter, so do not replay it concurrently with itself).  lm_forward_host uses plan-owned staging buffers and streams and is NOT
- *     re-entrant on one plan.
+ *   - a plan's tables are immutable after creation: concurrent lm_forward calls from any threads on any
+ *     streams are safe.  Each launch takes the next of 1024 plan-owned scheduling slots (a work counter
+ *     and the small-batch scratch); the kernel leaves its slot zeroed, so a launch needs no memset and
+ *     launches on one stream can never collide.  Only more than 1024 launches of ONE plan in flight at
+ *     the same time on different streams could share a slot.  A launch captured in a CUDA graph keeps
+ *     its slot: do not replay one captured launch concurrently with itself.
+ *   - lm_forward_host / lm_forward_host_pcm16 use plan-owned staging buffers and streams; concurrent
+ *     callers on one plan are serialised inside the library (a mutex), so they are safe, not parallel:
+ *     use one plan per thread to overlap host pipelines.
  *   - there is no CPU fallback anywhere: without a CUDA device lm_plan_create fails.
  */
 #ifndef LOGMEL_B200_H
@@ -106,7 +110,8 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** plan);
 int lm_plan_destroy(lm_plan* plan);
 int lm_plan_frames(const lm_plan* plan);
 int lm_plan_info(const lm_plan* plan, lm_info* info);
-/* Tuning knobs for experiments: key "tma" (0/1), "max_ctas" (0 = SM count). */
+/* Tuning knobs for experiments: key "tma" (0/1), "max_ctas" (0 = SM count), "split" (small-batch mode:
+ * 0 = automatic, 1 = off, k = at most k tile ranges per clip), "host_chunk_clips", "stagger_ns". */
 int lm_plan_set(lm_plan* plan, const char* key, int value);
 /* Number of kernels this plan has launched since creation (lm_forward: 1 per call,
  * lm_forward_host: 1 per chunk, lm_forward_host_pcm16: 2 per chunk). */
@@ -172,6 +177,13 @@ int lm_resample(const lm_resampler* r, const float* in, int64_t in_len, float* o
  * in + i * in_stride and goes to out + i * out_stride (strides in floats). */
 int lm_resample_rows(const lm_resampler* r, const float* in, int64_t in_len, int64_t in_stride, int32_t n_rows,
                      float* out, int64_t out_stride, void* cuda_stream);
+
+/*
+ * T.AmplitudeToDB() as a stand-alone transform (R/src/data/preprocessing.py:46; torchaudio/functional/functional.py:390-391,
+ * stype "power", top_db None): out = multiplier * log10(max(in, amin)) - db_offset, element-wise.  Device pointers, in == out
+ * allowed.  Serves the `amplitude_to_db` attribute of the drop-in AudioPreprocessor.
+ */
+int lm_amplitude_to_db(const float* in, float* out, int64_t n, float multiplier, float amin, float db_offset, void* cuda_stream);
 
 /*
  * 16-bit PCM -> fp32 in [-1, 1): x / 32768, what torchaudio.load(normalize=True) hands the reference for a

@@ -9,7 +9,7 @@ import torch
 import audio_classification_icbhi_b200 as A
 from audio_classification_icbhi_b200 import wavio
 from oracle import logmel_oracle as O
-from tests.golden.make_golden import golden_input
+from tests.golden.make_golden import PLAIN_CASES, golden_input
 
 pytestmark = pytest.mark.gpu
 NORM_ATOL = 2e-4
@@ -268,3 +268,65 @@ def test_randomised_geometries_match_oracle():
             ref = O.normalize(db)
             assert np.abs(out[i] - ref).max() < NORM_ATOL, (trial, n_fft, hop, n_mels, T, lens[i])
         plan.close()
+
+
+def test_forked_workers_decode_and_the_gpu_resamples_and_collates(tmp_path):
+    """The training-loop pattern of INTEGRATION.md section 3 with real forked workers: 44.1 / 4 / 10 kHz recordings are
+    decoded in the workers (no CUDA there), resampled and turned into features in this process, one launch per batch."""
+    d = tmp_path / "audio_and_txt_files"
+    d.mkdir()
+    rs = np.random.RandomState(6)
+    rates = [44100, 4000, 10000, 16000, 44100, 16000]
+    sigs = []
+    for i, sr in enumerate(rates):
+        x = (rs.standard_normal(sr * 2) * 0.1).clip(-1, 1)
+        sigs.append(x)
+        wavio.write_wav_pcm16(str(d / f"{100 + i}_r.wav"), x, sr)
+        (d / f"{100 + i}_r.txt").write_text(f"0.0\t1.0\t{i % 2}\t0\n")
+    cfg = {"data": dict(sample_rate=16000, n_mels=128, n_fft=2048, hop_length=512, duration=3.0)}
+    ds = A.ICBHIDataset(tmp_path, "test", cfg)
+    ds.data = [(str(d / f"{100 + i}_r.wav"), i % 2) for i in range(6)]
+    torch.cuda.init()
+    _ = ds.preprocessor.plan                                  # the parent owns a CUDA context before the fork
+    loader = torch.utils.data.DataLoader(ds.raw(), batch_size=3, num_workers=2, collate_fn=A.raw_collate,
+                                         multiprocessing_context="fork")
+    feats, labels = [], []
+    launches0 = ds.preprocessor.plan.launches
+    for f, y in A.GpuLoader(loader, A.GpuCollate(ds.preprocessor)):
+        assert f.is_cuda and f.shape == (3, 1, 128, 94)
+        feats.append(f)
+        labels += y.tolist()
+    assert ds.preprocessor.plan.launches - launches0 == 2 and labels == [0, 1, 0, 1, 0, 1]
+    feats = torch.cat(feats).cpu().numpy()
+    for i, sr in enumerate(rates):
+        xq = (np.rint(sigs[i] * 32767) / 32768.0).astype(np.float32)
+        x16 = xq if sr == 16000 else O.resample(xq, sr, 16000).astype(np.float32)
+        assert np.abs(feats[i, 0] - O.logmel(x16, O.OracleConfig(duration=3.0))).max() < NORM_ATOL
+
+
+def test_transform_attributes_of_the_reference_class(golden):
+    """The reference object exposes its torchaudio transforms as attributes (R/src/data/preprocessing.py:38-53); callers
+    such as tests/golden/make_golden.py use them directly.  Here they are GPU-backed: mel_spectrogram against the
+    reference's mel power, amplitude_to_db against its dB stage, the masks against torchaudio's own draws."""
+    p = A.AudioPreprocessor(augment=True)
+    for name, seed, n in (("headline_5s", 1, 80000), ("short_1p3s_pad_5s", 2, 20800)):
+        case = [c for c in PLAIN_CASES if c[0] == name][0]
+        w = p.pad_or_crop(torch.from_numpy(golden_input(case[3], case[4], case[5])).unsqueeze(0))
+        melp = p.mel_spectrogram(w)
+        assert melp.device.type == "cpu" and tuple(melp.shape) == (1, 128, 157)
+        ref = golden[f"{name}/mel_power"]
+        floor = max(1e-6 * np.abs(ref).max(), 1e-30)
+        assert (np.abs(melp[0].numpy() - ref) / np.maximum(np.abs(ref), floor)).max() < 1e-4
+        db = p.amplitude_to_db(torch.from_numpy(ref).unsqueeze(0))
+        assert np.abs(db[0].numpy() - golden[f"{name}/db"]).max() < 1e-4
+        assert np.abs(p.normalize(db)[0].numpy() - golden[f"{name}/norm"]).max() < NORM_ATOL
+    x = torch.randn(1, 48000) * 0.1                     # another length: the attribute neither pads nor crops
+    assert tuple(p.mel_spectrogram(x).shape) == (1, 128, 94)
+    import torchaudio.transforms as T
+    spec = torch.randn(1, 128, 157)
+    torch.manual_seed(3)
+    a = p.time_mask(p.freq_mask(spec))
+    torch.manual_seed(3)
+    b = T.TimeMasking(time_mask_param=35)(T.FrequencyMasking(freq_mask_param=15)(spec))
+    assert torch.equal(a, b)
+    assert not hasattr(A.AudioPreprocessor(augment=False), "freq_mask")       # as in the reference: only with augment

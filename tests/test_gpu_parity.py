@@ -466,3 +466,43 @@ def test_non_hann_window_is_refused(A):
     with pytest.raises(RuntimeError, match="unsupported"):
         A.LogMelPlan(window=torch.hamming_window(2048), device="cuda:0")
     A.LogMelPlan(window=torch.hann_window(2048), device="cuda:0").close()
+
+
+def test_seeded_training_batches_of_32_and_64_in_one_launch(A, golden):
+    """BASELINE configs[3] at its stated size: batch 32 (R/config_segmented.yaml:21) and 64 (README) of 3 s clips with
+    the reference's seeded noise / roll / SpecAugment choices, each as ONE kernel launch, against values the reference
+    classes produced for the same 64 clips (tests/golden/make_golden.py, aug64_3s) and against the float64 oracle."""
+    cfg = O.OracleConfig(duration=3.0)
+    plan = get_plan(A, 2048, 512, cfg.target_length)
+    trace, pos = golden["aug64_3s/trace"], golden["aug64_3s/pos"]
+    draws = O.replay_augmentation(np.random.RandomState(42), O.TorchCpuGenerator(42), 64, cfg.target_length,
+                                  cfg.n_mels, cfg.frames, want_noise_values=True)
+    aug = A.make_aug_array(64)
+    noise = np.zeros((64, cfg.target_length), dtype=np.float32)
+    clips = []
+    for c, d in enumerate(draws):
+        aug[c]["shift"] = d.shift
+        aug[c]["noise_scale"] = 0.005 if d.noise else 0.0
+        aug[c]["f0"], aug[c]["f1"], aug[c]["t0"], aug[c]["t1"] = d.f0, d.f1, d.t0, d.t1
+        if d.noise:
+            noise[c] = d.noise_values
+        clips.append(golden_input(100 + c, cfg.target_length))
+    launches0 = plan.launches
+    got64 = run_clips(plan, clips, aug=aug, noise=noise)
+    got32 = run_clips(plan, clips[:32], aug=aug[:32], noise=noise[:32])
+    assert plan.launches - launches0 == 2          # one launch per batch
+    np.testing.assert_array_equal(got32["out"], got64["out"][:32])   # a clip does not depend on its batch
+    for c, d in enumerate(draws):
+        flat = got64["out"][c].reshape(-1)
+        assert np.abs(flat[pos] - golden["aug64_3s/samples"][c]).max() < NORM_ATOL
+        assert abs(np.abs(flat).mean() - golden["aug64_3s/absmean"][c]) < 1e-4
+        z = got64["db"][c] == 0.0
+        rows, cols = np.nonzero(z.all(axis=1))[0], np.nonzero(z.all(axis=0))[0]
+        f0, f1 = (rows[0], rows[-1] + 1) if len(rows) else (0, 0)
+        t0, t1 = (cols[0], cols[-1] + 1) if len(cols) else (0, 0)
+        assert [f0, f1, t0, t1] == list(trace[c][2:])                 # mask indices bit-exact
+    for c in (5, 17, 40, 63):                                          # full feature maps against the oracle
+        d = draws[c]
+        ref = O.logmel(clips[c], cfg, shift=d.shift, noise=d.noise_values, noise_scale=0.005 if d.noise else 0.0,
+                       masks=(d.f0, d.f1, d.t0, d.t1))
+        assert np.abs(got64["out"][c] - ref).max() < NORM_ATOL

@@ -143,8 +143,8 @@ def test_icbhi_dataset_discovery_and_splits(tmp_path):
     assert tr.preprocessor.target_length == 48000
     assert [l for _, l in tr.data] == [0, 1, 2, 3, 0, 1, 2]          # union of cycle flags per recording
     assert A.ICBHIDataset.CLASS_MAP == {"normal": 0, "crackles": 1, "wheezes": 2, "both": 3}
-    w, y = tr.raw_item(1)
-    assert w.shape == (1, 48000) and y == 1
+    w, sr, y = tr.raw_item(1)
+    assert w.shape == (1, 48000) and sr == 16000 and y == 1
     assert len(tr.raw()) == 7
     with pytest.raises(ValueError, match="Audio directory not found"):
         A.ICBHIDataset(tmp_path / "nope", "train")
@@ -185,3 +185,28 @@ def test_shard_bounds_cover_everything_once():
                 seen.extend(range(lo, hi))
             assert seen == list(range(n))
     assert A.shard_bounds(6900, 7, 8) == (6041, 6900) and A.shard_size(6900, 8) == 863
+
+
+def test_raw_items_never_touch_cuda_even_when_the_file_needs_resampling(tmp_path):
+    """raw mode is what forked DataLoader workers run, and raw ICBHI recordings are 4 / 10 / 44.1 kHz.
+    raw_item must therefore only decode: it hands back the file's own rate and leaves resampling to GpuCollate in
+    the process that owns the CUDA context.  This test runs where there is no GPU at all, through real forked
+    workers and the identity collate."""
+    import torch
+    d = tmp_path / "audio_and_txt_files"
+    d.mkdir()
+    rs = np.random.RandomState(5)
+    rates = [44100, 4000, 10000, 16000]
+    for i, sr in enumerate(rates):
+        wavio.write_wav_pcm16(str(d / f"{100 + i}_r.wav"), (rs.standard_normal(sr * 2) * 0.1).clip(-1, 1), sr)
+        (d / f"{100 + i}_r.txt").write_text("0.0\t1.0\t0\t1\n")
+    cfg = {"data": dict(sample_rate=16000, n_mels=128, n_fft=2048, hop_length=512, duration=3.0)}
+    ds = A.ICBHIDataset(tmp_path, "train", cfg)            # 70 % of 4 = 2 recordings... take the raw view of all
+    ds.data = [(str(d / f"{100 + i}_r.wav"), 2) for i in range(4)]
+    w, sr, y = ds.raw_item(0)
+    assert (tuple(w.shape), sr, y) == ((1, 88200), 44100, 2) and w.device.type == "cpu"
+    assert ds.preprocessor._plan is None                    # no plan, no CUDA context was created
+    loader = torch.utils.data.DataLoader(ds.raw(), batch_size=2, num_workers=2, collate_fn=A.raw_collate,
+                                         multiprocessing_context="fork")
+    got = [item for batch in loader for item in batch]
+    assert [(int(w.shape[-1]), sr) for w, sr, _ in got] == [(2 * r, r) for r in rates]

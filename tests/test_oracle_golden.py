@@ -146,3 +146,44 @@ def test_oracle_resample_matches_torchaudio_golden(sr):
     assert np.abs(y - g[f"out/{sr}"]).max() < 1e-5
     k, width, o, q = O.sinc_resample_kernel(sr, 16000)
     assert k.shape == (q, 2 * width + o)
+
+
+def test_seeded_64_clip_trace_is_bit_exact(golden):
+    """BASELINE configs[3] at its stated size (batch 32 / 64, R/config_segmented.yaml:21): the draw replay stays in
+    step with the reference over 64 consecutive clips (28 of them consume 48 000 normal draws each), and the
+    oracle reproduces the 64 sampled output values the fixture keeps per clip."""
+    cfg = O.OracleConfig(duration=3.0)
+    trace = golden["aug64_3s/trace"]
+    assert trace.shape == (64, 6) and int(trace[:, 0].sum()) == 28
+    draws = O.replay_augmentation(np.random.RandomState(42), O.TorchCpuGenerator(42), 64, cfg.target_length,
+                                  cfg.n_mels, cfg.frames, want_noise_values=True)
+    canon = lambda a, b: (a, b) if b > a else (0, 0)
+    got = np.array([[int(d.noise), d.shift, *canon(d.f0, d.f1), *canon(d.t0, d.t1)] for d in draws])
+    np.testing.assert_array_equal(got, trace)
+    np.testing.assert_array_equal(trace[:6], golden["aug_3s/trace"])   # same seeds: the 6-clip trace is its prefix
+    pos = golden["aug64_3s/pos"]
+    for c in (0, 1, 31, 32, 63):
+        d = draws[c]
+        out = O.logmel(golden_input(100 + c, cfg.target_length), cfg, shift=d.shift, noise=d.noise_values,
+                       noise_scale=0.005 if d.noise else 0.0, masks=(d.f0, d.f1, d.t0, d.t1))
+        assert np.abs(out.reshape(-1)[pos] - golden["aug64_3s/samples"][c]).max() < NORM_ATOL
+        assert abs(np.abs(out).mean() - golden["aug64_3s/absmean"][c]) < 1e-4
+
+
+@pytest.mark.parametrize("case", PLAIN_CASES, ids=[c[0] for c in PLAIN_CASES])
+def test_torchaudio_port_reproduces_reference_outputs(golden, case):
+    """oracle/torchaudio_port.py is bench.py's CPU baseline and `--impl reference` arm (the reference classes cannot
+    travel to the GPU box).  It must BE the reference's arithmetic: same torchaudio objects, same call order --
+    so its outputs equal the reference-generated goldens exactly."""
+    torch = pytest.importorskip("torch")
+    pytest.importorskip("torchaudio")
+    from oracle.torchaudio_port import ReferencePipeline
+    name, cls, kw, seed, n, kind = case
+    torch.set_num_threads(1)
+    ref = ReferencePipeline(duration=kw["duration"], flexible=(cls == "flex"))
+    meta = golden[f"{name}/meta"]
+    assert (ref.n_fft, ref.hop_length, ref.target_length) == tuple(meta[:3])
+    w = torch.from_numpy(golden_input(seed, n, kind)).unsqueeze(0)
+    np.testing.assert_array_equal(ref.mel_power(w)[0].numpy(), golden[f"{name}/mel_power"])
+    np.testing.assert_array_equal(ref(w)[0].numpy(), golden[f"{name}/norm"])
+    np.testing.assert_array_equal(ref.batched(w)[0, 0].numpy(), golden[f"{name}/norm"])
