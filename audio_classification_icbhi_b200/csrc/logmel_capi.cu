@@ -12,6 +12,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
+
 #include "logmel_kernel.cuh"
 #include "logmel_aux.cuh"
 
@@ -41,6 +43,12 @@ struct DeviceOf {
         if (dev >= 0 && dev != prev) cudaSetDevice(dev); else dev = -1;
     }
     ~DeviceOf() { if (dev >= 0 && prev >= 0) cudaSetDevice(prev); }
+};
+
+// NVTX range around a C-ABI entry point (ranges around plan / execute), visible in Nsight Systems / Compute
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 constexpr int kSlots = 3;   // host pipeline depth
@@ -156,8 +164,10 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     }
     const int grid = std::min<int>(B * k.split, cap);
     const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
+    const bool device_noise = (aug != nullptr) && (noise == nullptr);   // clips may ask for Philox noise drawn in the kernel
     if (p->n_fft == 2048) {
         if (extra) lm::logmel_kernel<2048, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+        else if (device_noise) lm::logmel_kernel<2048, false, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
         else lm::logmel_kernel<2048, false><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
     } else {
         if (extra) lm::logmel_kernel<1024, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
@@ -206,6 +216,7 @@ const char* lm_strerror(int status) {
 const char* lm_last_cuda_error(void) { return g_cuda_err; }
 
 int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
+    NvtxRange nvtx("lm_plan_create");
     if (!cfg || !out_plan || !cfg->window || !cfg->fb) return LM_ERR_INVALID_ARG;
     *out_plan = nullptr;
     if (cfg->n_fft != 2048 && cfg->n_fft != 1024) return LM_ERR_UNSUPPORTED;
@@ -364,6 +375,9 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(lm::logmel_kernel<2048, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(p->smem_bytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm::logmel_kernel<2048, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(p->smem_bytes));
     } else {
         p->smem_bytes = lm::Smem<1024>::total(p->ns, p->n_dk);
         e = cudaFuncSetAttribute(lm::logmel_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -421,6 +435,7 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
     if (!plan || B < 0) return LM_ERR_INVALID_ARG;
     if (B == 0) return LM_OK;
     if (!wave || !offset || !length || !out_norm) return LM_ERR_INVALID_ARG;
+    NvtxRange nvtx("lm_forward");
     int dev = -1;
     LM_CUDA(cudaGetDevice(&dev));
     if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
@@ -630,6 +645,7 @@ static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, in
     if (!wave || !offset || !length || !out) return LM_ERR_INVALID_ARG;
     for (int i = 0; i < B; ++i)
         if (length[i] < 0 || offset[i] < 0 || offset[i] + length[i] > total_samples) return LM_ERR_INVALID_ARG;
+    NvtxRange nvtx(pcm16 ? "lm_forward_host_pcm16" : "lm_forward_host");
     std::lock_guard<std::mutex> one_caller(plan->host_mu);   // the staging slots belong to the plan
     int dev = -1;
     LM_CUDA(cudaGetDevice(&dev));

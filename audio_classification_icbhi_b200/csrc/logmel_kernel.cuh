@@ -330,6 +330,38 @@ __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[
     lm_fft32_soa(pr, pi, xr, xi);
 }
 
+// The four normals of one Philox block: z[j] == philox_normal(seed, 4 * blk + j), bit for bit (same operations),
+// for the staging of noisy clips, which walks four consecutive samples per thread: one block serves up to four
+// samples and one log / sincos serves two of them.
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t blk, float (&z)[4]) {
+    uint32_t c0 = blk, c1 = 0u, c2 = 0x6c6f676du, c3 = 0x656c0000u;
+    uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t a = h ? c2 : c0, b = h ? c3 : c1;
+        const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float r = sqrtf(-2.0f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        z[2 * h] = r * cs;
+        z[2 * h + 1] = r * sn;
+    }
+}
+
+struct ClipCtx;
+// Staging of one tile of a clip with on-device Philox noise (gain, roll, reflect padding as in stage_gather): four
+// consecutive slots per thread, so one Philox block serves up to four samples.  Kept out of line: it is the rare
+// path and must not change the register allocation or the code layout of the kernel's main loop.
+__device__ __noinline__ void stage_noisy_tile(const ClipCtx& c, float* __restrict__ sb, int ns, int need, int j0, int T, int gtid);
+
 template <int NFFT>
 struct Geo {
     static constexpr int FPW = (NFFT == 2048) ? 1 : 2;   // frames per warp pass
@@ -375,6 +407,36 @@ struct alignas(16) ClipCtx {
     int clip;            // index of the clip in the batch; -1 in the "next clip" slot = the batch is exhausted
     int t_begin, t_end;  // tile range of this virtual clip
 };
+__device__ __noinline__ void stage_noisy_tile(const ClipCtx& c, float* __restrict__ sb, int ns, int need, int j0, int T, int gtid) {
+    const float* __restrict__ src = c.src;
+    const int shift = c.shift, lc = c.lc;
+    const float gain = c.gain, nscale = c.nscale;
+    const uint64_t seed = c.seed;
+    for (int q = gtid; 4 * q < ns; q += kGroupThreads) {
+        float v4[4], zc[4];
+        uint32_t blk_c = 0xffffffffu;   // block held in zc
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = 4 * q + k;
+            int j = j0 + e;
+            if (j < 0) j = -j;
+            else if (j >= T) j = 2 * (T - 1) - j;
+            float v = 0.0f;
+            if (e < need && j >= 0 && j < T) {
+                int i = j - shift;               // torch.roll: out[j] = in[(j - shift) mod T]
+                if (i < 0) i += T;
+                else if (i >= T) i -= T;
+                if (i < lc) v = __ldg(src + i) * gain;
+                const uint32_t blk = static_cast<uint32_t>(i) >> 2;
+                if (blk != blk_c) { philox_normal4(seed, blk, zc); blk_c = blk; }
+                const float z = (i & 2) ? ((i & 1) ? zc[3] : zc[2]) : ((i & 1) ? zc[1] : zc[0]);
+                v = fmaf(z, nscale, v);
+            }
+            v4[k] = v;
+        }
+        *reinterpret_cast<float4*>(sb + 4 * q) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    }
+}
 constexpr int kCtxSlot = 80;
 static_assert(sizeof(ClipCtx) <= kCtxSlot && kCtxSlot % 16 == 0, "ClipCtx slot size");
 
@@ -420,7 +482,10 @@ __device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* 
     c->silent_from = silent_from;
 }
 
-template <int NFFT, bool EXTRA_OUT>
+// FASTNOISE: tiles of clips with on-device Philox noise are staged four samples per thread (stage_noisy_tile).  The call
+// costs the main loop ~3 % (registers live across it), so the host launches this instantiation only when the batch can
+// contain such clips (augmentation records given, no host-drawn noise tensor); the headline path keeps FASTNOISE = false.
+template <int NFFT, bool EXTRA_OUT, bool FASTNOISE = false>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     using G = Geo<NFFT>;
     constexpr int TILE_F = G::TILE_F;
@@ -525,6 +590,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         const int j0 = tf * hop - HALF;
         // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
         // feed only frames >= `frames` and are zeroed
+        if (FASTNOISE && c.nscale != 0.0f && c.nz == nullptr && cnt == 0) {   // on-device noise (training batches): out of line
+            stage_noisy_tile(*cc, sb, p.ns, need, j0, T, gtid);   // the context in shared memory, not the register copy
+            return true;
+        }
         for (int idx = gtid; idx < rest; idx += kGroupThreads) {
             const int e = idx < e_lo ? idx : idx + cnt;
             int j = j0 + e;

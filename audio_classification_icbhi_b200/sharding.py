@@ -76,7 +76,12 @@ class FusedGather:
     has a multicast address (the switch replicates it), plain stores to the peers' mapped buffers
     otherwise -- so the transfer overlaps the compute of the remaining clips.  `finish` is the rank
     barrier after which `self.full` holds all ranks' features.  NCCL (`ShardedLogMel.gathered`) remains
-    the path for ranks without peer access."""
+    the path for ranks without peer access.
+
+    Ordering: `run` also STARTS with a rank barrier on the current stream.  The kernel writes straight into the
+    other ranks' `full` buffers, so a rank must not begin step k+1 while a slower rank's consumer kernels (enqueued
+    on that rank's stream after `finish`) still read step k: the entry barrier orders every rank's earlier stream
+    work before anybody's stores.  `self.full` is therefore valid from `finish()` until this rank's next `run()`."""
 
     def __init__(self, plan, per_rank: int, group=None, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm
@@ -105,6 +110,7 @@ class FusedGather:
     def run(self, wave: torch.Tensor, offset: torch.Tensor, length: torch.Tensor, **kw) -> None:
         if int(offset.numel()) > self.per_rank:
             raise ValueError("more clips than the rank's slice holds")
+        self._hdl.barrier()   # write-after-read: peers may still be reading the previous step's features
         self.plan.forward_gather(wave, offset, length, self.out_slice_ptr, self.peer_slice_ptrs, self.mc_slice_ptr, **kw)
 
     def finish(self) -> torch.Tensor:

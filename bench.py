@@ -11,8 +11,13 @@ over that batch = one launch of the fused kernel.  With N > 1 every rank owns it
 time over ranks.  The optional NCCL all-gather of the features is timed separately ("gathered").
 
 Extra keys of the line: `e2e` (lm_forward_host, pinned fp32 host buffers in, host features out),
-`e2e_pcm16` (the same clips as 16-bit PCM), `ragged_corpus` and `analyzer_windows` (BASELINE configs[2]
-and [4] on one GPU, device-resident), `gathered` (N > 1: NCCL all-gather and the in-kernel fused gather).
+`e2e_pcm16` (the same clips as 16-bit PCM), and the other BASELINE.json configs as stated there:
+`latency_single_clip_us` (configs[0]), `strong_scaling` (configs[1]: 4096 clips in TOTAL over the N ranks),
+`ragged_corpus` (configs[2]: 6900 cycles sharded over the ranks, features gathered in-kernel), `train_batch`
+(configs[3]: batches of 32 / 64 augmented 3 s clips), `analyzer_windows` (configs[4]: 7200 windows of a 1-hour
+recording sharded over the ranks and gathered), `gathered` (N > 1: NCCL all-gather vs the in-kernel fused gather
+of the headline batch).  Every multi-GPU result is compared bit for bit with the single-GPU result of rank 0 and
+the run EXITS NON-ZERO on a mismatch: the driver's scaling run is parity evidence, not only a timing.
 
 `--impl reference` times the reference's CPU implementation of the same path (the torchaudio
 glue in oracle/torchaudio_port.py, all host threads) on a bounded sample of the same workload.
@@ -214,6 +219,250 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configs.  Timing: CUDA events on the launching stream, >= 3 warm-up launches, max over
+# ranks; inputs of the big configs exceed the 126 MB L2, the small ones (configs[0], [3]) are timed L2-warm and,
+# separately, after a 256 MB L2 flush.
+# ---------------------------------------------------------------------------------------------------------------
+NVLINK_PEER_GBS = 770.0   # measured peer-copy rate per direction on this pool (B200_PROFILING.md)
+
+
+def _timed(fn, reps=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def _max_over_ranks(ms, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sharded_gathered(plan, wave, offset, length, n_total, world, rank, dev, failures, tag, reps=10):
+    """Shard `n_total` items by index over the ranks (shard_bounds), gather the features into every rank's buffer
+    in-kernel (FusedGather) and compare with rank 0 extracting everything alone.  Returns (ms max over ranks, mode)."""
+    import torch
+    import torch.distributed as dist
+    from audio_classification_icbhi_b200 import shard_bounds, shard_size
+    if world == 1:
+        out = torch.empty(plan.out_shape(n_total), device=dev)
+        return _timed(lambda: plan.forward(wave, offset, length, out=out), reps), "one GPU, no gather", out
+    from audio_classification_icbhi_b200 import FusedGather
+    per = shard_size(n_total, world)
+    lo, hi = shard_bounds(n_total, rank, world)
+    fg = FusedGather(plan, per)
+    off_r, len_r = offset[lo:hi].contiguous(), length[lo:hi].contiguous()
+
+    def step():
+        fg.run(wave, off_r, len_r)
+        fg.finish()
+
+    ms = _max_over_ranks(_timed(step, reps), world, dev)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:   # the whole job on one GPU must give the same bits
+        alone = plan.forward(wave, offset, length)
+        torch.cuda.synchronize()
+        for r in range(world):
+            a, b = shard_bounds(n_total, r, world)
+            if not torch.equal(fg.full[r * per:r * per + (b - a)], alone[a:b]):
+                failures.append(f"{tag}: gathered shard of rank {r} differs from the single-GPU result")
+        del alone
+    dist.barrier()
+    return ms, "lm_forward_gather: " + fg.mode, None
+
+
+def corpus_config(plan, world, rank, dev, peak, failures):
+    """configs[2]: ICBHI-sized ragged corpus, 6900 cycles of lognormal length (pad / crop to 5 s), replicated input,
+    cycles sharded ceil(6900 / N) per rank, features gathered to every rank."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(0)
+    secs = np.clip(rs.lognormal(np.log(2.5), 0.5, 6900), 0.2, 16.2)
+    lens = (secs * 16000).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum((lens + 3) // 4 * 4)[:-1]])
+    g = torch.Generator(device=dev).manual_seed(1)
+    wave = torch.randn(int(starts[-1] + lens[-1]) + 4, generator=g, device=dev) * 0.1
+    off, ln = torch.from_numpy(starts).to(dev), torch.from_numpy(lens.astype(np.int32)).to(dev)
+    ms, mode, _ = _sharded_gathered(plan, wave, off, ln, 6900, world, rank, dev, failures, "configs[2] corpus")
+    algo = int((4 * np.minimum(lens, T_LEN)).sum() + 6900 * 4 * 128 * plan.frames)   # read once + written once
+    per_rank_in = int(6900 * 4 * 128 * plan.frames * (world - 1) / world)
+    res = {"workload": "configs[2]: 6900 cycles, lognormal 0.2-16.2 s (mean %.2f s), pad/crop to 5 s, sharded over %d rank(s)" % (secs.mean(), world),
+           "ms": ms, "clips_per_s": 6900 / ms * 1e3, "collective": mode,
+           "algorithmic_bytes": algo, "hbm_frac_per_gpu": algo / world / (ms * 1e-3) / 1e9 / peak}
+    if world > 1:
+        res.update({"gather_bytes_received_per_rank": per_rank_in, "nvlink_in_gbs": per_rank_in / (ms * 1e-3) / 1e9,
+                    "nvlink_frac": per_rank_in / (ms * 1e-3) / 1e9 / NVLINK_PEER_GBS, "matches_single_gpu": not failures})
+    return res
+
+
+def windows_config(world, rank, dev, peak, failures):
+    """configs[4]: 1-hour recording, 1 s windows at 50 % overlap -> 7200 windows; the recording is replicated, the
+    windows are sharded by index (900 per rank at N = 8) and the features gathered."""
+    import torch
+    from audio_classification_icbhi_b200 import LogMelPlan, segment_offsets
+    plan_w = LogMelPlan(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=128, target_length=16000, device=dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    rec = torch.randn(3600 * 16000, generator=g, device=dev) * 0.1
+    ws, wl, _ = segment_offsets(int(rec.numel()), 16000, 1.0, 0.5)
+    off, ln = torch.from_numpy(ws).to(dev), torch.from_numpy(wl).to(dev)
+    ms, mode, _ = _sharded_gathered(plan_w, rec, off, ln, len(ws), world, rank, dev, failures, "configs[4] windows")
+    algo = int(len(ws) * (4 * 16000 + 4 * 128 * plan_w.frames))     # every window reads its own second and writes 16 KB
+    per_rank_in = int(len(ws) * 4 * 128 * plan_w.frames * (world - 1) / world)
+    res = {"workload": "configs[4]: 1 h @ 16 kHz, 1 s windows, 50 %% overlap -> 7200 windows [7200,1,128,32], sharded over %d rank(s)" % world,
+           "ms": ms, "windows_per_s": len(ws) / ms * 1e3, "audio_seconds_per_s": 3600.0 / (ms * 1e-3), "collective": mode,
+           "algorithmic_bytes": algo, "hbm_frac_per_gpu": algo / world / (ms * 1e-3) / 1e9 / peak}
+    if world > 1:
+        res.update({"gather_bytes_received_per_rank": per_rank_in, "nvlink_in_gbs": per_rank_in / (ms * 1e-3) / 1e9,
+                    "nvlink_frac": per_rank_in / (ms * 1e-3) / 1e9 / NVLINK_PEER_GBS, "matches_single_gpu": not failures})
+    plan_w.close()
+    return res
+
+
+def strong_scaling(plan, clips, world, rank, dev, peak, failures):
+    """configs[1] as a fixed job: 4096 clips in TOTAL, 4096 / N per rank (512 at N = 8 = 1.7 rounds of the 296 groups),
+    features left sharded (the data-parallel consumer).  value = 4096 / max-over-ranks time."""
+    import torch
+    from audio_classification_icbhi_b200 import shard_bounds
+    lo, hi = shard_bounds(BATCH, rank, world)
+    n = hi - lo
+    sub = clips[:n].contiguous().view(-1)        # this rank's share (any clips do: the work is data independent)
+    off = torch.arange(n, device=dev, dtype=torch.int64) * T_LEN
+    ln = torch.full((n,), T_LEN, device=dev, dtype=torch.int32)
+    out = torch.empty(plan.out_shape(n), device=dev)
+    ms = _max_over_ranks(_timed(lambda: plan.forward(sub, off, ln, out=out), 20), world, dev)
+    algo = plan.bytes_per_clip * BATCH
+    return {"workload": f"configs[1] as a fixed job: 4096 clips total, {n} per rank, features left sharded",
+            "ms": ms, "value": BATCH / ms * 1e3, "unit": UNIT, "hbm_frac_per_gpu": algo / world / (ms * 1e-3) / 1e9 / peak}
+
+
+def latency_config(plan, dev):
+    """configs[0]: ONE 5 s clip -> [1,1,128,157]; the small-batch mode spreads its 20 tiles over 20 SMs.  p50 / p90 of
+    300 launches: eager (lm_forward per call), replayed from a CUDA graph, and eager after an L2 flush (cold input)."""
+    import torch
+    clip = synth_clips(1, 77, device=dev).view(-1)
+    off = torch.zeros(1, device=dev, dtype=torch.int64)
+    ln = torch.full((1,), T_LEN, device=dev, dtype=torch.int32)
+    out = torch.empty(plan.out_shape(1), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def series(launch, n=300, cold=False):
+        ts = []
+        for _ in range(n):
+            if cold:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            launch()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts.sort()
+        return {"p50": round(ts[len(ts) // 2], 2), "p90": round(ts[int(0.9 * len(ts))], 2), "launches": n}
+
+    eager = lambda: plan.forward(clip, off, ln, out=out)
+    for _ in range(20):
+        eager()
+    torch.cuda.synchronize()
+    res = {"workload": "configs[0]: one 5 s clip, device-resident, CUDA-event timed per launch", "eager_l2_warm": series(eager)}
+    res["eager_l2_flushed"] = series(eager, 100, cold=True)
+    try:
+        s = torch.cuda.Stream(dev)
+        with torch.cuda.stream(s):
+            eager()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                eager()
+        torch.cuda.synchronize()
+        res["cuda_graph_l2_warm"] = series(graph.replay)
+    except Exception as e:
+        res["cuda_graph_l2_warm"] = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+    plan.set("split", 1)
+    res["without_small_batch_split"] = series(eager, 100)
+    plan.set("split", 0)
+    res["value"] = res["eager_l2_warm"]["p50"]
+    return res
+
+
+def train_batch_config(dev, peak):
+    """configs[3]: the training-time path at the reference's batch sizes (32: R/config_segmented.yaml:21, 64: README),
+    3 s clips, waveform augmentation (gain, roll, on-device Philox noise) + log-mel + SpecAugment masks + z-norm, one
+    launch per batch; augmentation records drawn on the host (fast mode) and uploaded inside the timed step."""
+    import numpy as np
+    import torch
+    from audio_classification_icbhi_b200 import LogMelPlan, draw_fast_augmentation
+    T3 = 48000
+    plan3 = LogMelPlan(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=128, target_length=T3, device=dev)
+    res = {"workload": "configs[3]: batch of B augmented 3 s clips -> [B,1,128,94], one launch, aug records drawn and uploaded per step"}
+    g = torch.Generator(device=dev).manual_seed(5)
+    rng = np.random.default_rng(3)
+    for B in (32, 64):
+        clips = torch.randn(B * T3, generator=g, device=dev) * 0.1
+        off = torch.arange(B, device=dev, dtype=torch.int64) * T3
+        ln = torch.full((B,), T3, device=dev, dtype=torch.int32)
+        out = torch.empty(plan3.out_shape(B), device=dev)
+        aug_d = plan3.upload_aug(draw_fast_augmentation(B, T3, 128, plan3.frames, rng=rng, gain_db=6.0))
+        ms_dev = _timed(lambda: plan3.forward(clips, off, ln, aug=aug_d, out=out), 200, 20)
+
+        def step():
+            a = plan3.upload_aug(draw_fast_augmentation(B, T3, 128, plan3.frames, rng=rng, gain_db=6.0))
+            plan3.forward(clips, off, ln, aug=a, out=out)
+
+        ms_step = _timed(step, 100, 10)
+        algo = B * (4 * T3 + 4 * 128 * plan3.frames)
+        res[f"B{B}"] = {"us_per_launch": round(ms_dev * 1e3, 2), "clips_per_s": B / ms_dev * 1e3,
+                        "clips_per_s_with_host_draws": B / ms_step * 1e3,
+                        "hbm_frac": algo / (ms_dev * 1e-3) / 1e9 / peak}
+    plan3.close()
+    return res
+
+
+def gathered_headline(plan, wave, offset, length, out, world, dev, args, failures):
+    """The headline batch with the features all-gathered to every rank: NCCL after the kernel vs the gather fused
+    into the kernel (multimem.st / peer stores).  A difference between the two is a parity failure."""
+    import torch
+    import torch.distributed as dist
+    from audio_classification_icbhi_b200 import FusedGather
+    full = torch.empty((world * BATCH, 1, 128, plan.frames), device=dev, dtype=torch.float32)
+    g_steps = max(1, min(args.steps, 10))
+
+    def nccl_step():
+        plan.forward(wave, offset, length, out=out)
+        dist.all_gather_into_tensor(full, out)
+
+    g_ms = _max_over_ranks(_timed(nccl_step, g_steps, 2), world, dev)
+    recv = int(out.numel() * 4 * (world - 1))
+    gathered = {"value": world * BATCH / (g_ms * 1e-3), "unit": UNIT, "collective": "nccl all_gather_into_tensor",
+                "bytes_received_per_rank": recv, "nvlink_in_gbs": recv / (g_ms * 1e-3) / 1e9}
+    fg = FusedGather(plan, BATCH)
+
+    def fused_step():
+        fg.run(wave, offset, length)
+        fg.finish()
+
+    f_ms = _max_over_ranks(_timed(fused_step, g_steps, 2), world, dev)
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(fg.full, full))
+    if not ok:
+        failures.append("headline batch: fused in-kernel gather differs from the NCCL all-gather")
+    gathered["fused"] = {"value": world * BATCH / (f_ms * 1e-3), "unit": UNIT, "collective": "lm_forward_gather: " + fg.mode,
+                         "matches_nccl_gather": ok, "nvlink_in_gbs": recv / (f_ms * 1e-3) / 1e9,
+                         "nvlink_frac": recv / (f_ms * 1e-3) / 1e9 / NVLINK_PEER_GBS}
+    return gathered
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -315,99 +564,30 @@ def run_b200(args) -> None:
     pcm_ok = bool(torch.equal(host_out, pcm_ref.cpu()))
     del pcm_ref
 
-    # ---- the other BASELINE configs on one GPU, device-resident (secondary figures, rank 0 of a 1-GPU run) ------
+    # ---- the other BASELINE.json configs, as stated there (all ranks take part; parity failures are fatal) ----------
+    peak, peak_src = measured_hbm_peak()
     extra = {}
-    if world == 1:
-        import numpy as np
-        # configs[2]: ICBHI-sized ragged corpus, 6900 cycles of lognormal length, pad / crop to 5 s
-        rs = np.random.RandomState(0)
-        secs = np.clip(rs.lognormal(np.log(2.5), 0.5, 6900), 0.2, 16.2)
-        lens = (secs * 16000).astype(np.int64)
-        starts = np.concatenate([[0], np.cumsum((lens + 3) // 4 * 4)[:-1]])
-        g = torch.Generator(device=dev).manual_seed(1)
-        rwave = torch.randn(int(starts[-1] + lens[-1]) + 4, generator=g, device=dev) * 0.1
-        roff, rlen = torch.from_numpy(starts).to(dev), torch.from_numpy(lens.astype(np.int32)).to(dev)
-        rout = torch.empty(plan.out_shape(6900), device=dev)
-
-        def timed(fn, reps=10):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-
-        ms_r = timed(lambda: plan.forward(rwave, roff, rlen, out=rout))
-        extra["ragged_corpus"] = {"workload": "configs[2]: 6900 cycles, lognormal 0.2-16.2 s (mean %.2f s), pad/crop to 5 s" % secs.mean(),
-                                  "ms": ms_r, "clips_per_s": 6900 / ms_r * 1e3}
-        del rwave, rout
-        # configs[4]: 1-hour recording, 1 s windows at 50 % overlap -> 7200 windows (offsets into one buffer)
-        from audio_classification_icbhi_b200 import segment_offsets
-        plan_w = LogMelPlan(sample_rate=16000, n_fft=2048, hop_length=512, n_mels=128, target_length=16000, device=dev)
-        rec = torch.randn(3600 * 16000, generator=g, device=dev) * 0.1
-        ws, wl, _ = segment_offsets(int(rec.numel()), 16000, 1.0, 0.5)
-        woff, wlen = torch.from_numpy(ws).to(dev), torch.from_numpy(wl).to(dev)
-        wout = torch.empty(plan_w.out_shape(len(ws)), device=dev)
-        ms_w = timed(lambda: plan_w.forward(rec, woff, wlen, out=wout))
-        extra["analyzer_windows"] = {"workload": "configs[4]: 1 h @ 16 kHz, 1 s windows, 50 % overlap -> 7200 windows [7200,1,128,32]",
-                                     "ms": ms_w, "windows_per_s": len(ws) / ms_w * 1e3, "audio_seconds_per_s": 3600.0 / (ms_w * 1e-3)}
-        del rec, wout, plan_w
-
-    # ---- optional: features all-gathered to every rank (single consumer) -----------------------
-    gathered = None
+    failures = []
+    extra["strong_scaling"] = strong_scaling(plan, clips, world, rank, dev, peak, failures)
+    extra["ragged_corpus"] = corpus_config(plan, world, rank, dev, peak, failures)
+    extra["analyzer_windows"] = windows_config(world, rank, dev, peak, failures)
+    if rank == 0:
+        extra["latency_single_clip_us"] = latency_config(plan, dev)
+        extra["train_batch"] = train_batch_config(dev, peak)
+    gathered = gathered_headline(plan, wave, offset, length, out, world, dev, args, failures) if world > 1 else None
+    bad = torch.tensor([len(failures)], device=dev)
     if world > 1:
-        full = torch.empty((world * BATCH, 1, 128, plan.frames), device=dev, dtype=torch.float32)
-        for _ in range(2):
-            plan.forward(wave, offset, length, out=out)
-            dist.all_gather_into_tensor(full, out)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g_steps = max(1, min(args.steps, 10))
-        g0.record()
-        for _ in range(g_steps):
-            plan.forward(wave, offset, length, out=out)
-            dist.all_gather_into_tensor(full, out)
-        g1.record()
-        torch.cuda.synchronize()
-        g_ms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        gathered = {"value": world * BATCH * g_steps / (float(g_ms.item()) * 1e-3), "unit": UNIT,
-                    "collective": "nccl all_gather_into_tensor", "bytes_per_rank": int(out.numel() * 4)}
-
-    # ---- the same gather fused into the kernel: stores to peer / multicast memory from the epilogue ----------
-    if world > 1 and gathered is not None:
-        try:
-            from audio_classification_icbhi_b200 import FusedGather
-            fg = FusedGather(plan, BATCH)
-            for _ in range(2):
-                fg.run(wave, offset, length)
-                fg.finish()
-            barrier()
-            f_ok = bool(torch.equal(fg.full, full))
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(g_steps):
-                fg.run(wave, offset, length)
-                fg.finish()
-            f1.record()
-            torch.cuda.synchronize()
-            f_ms = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
-            dist.all_reduce(f_ms, op=dist.ReduceOp.MAX)
-            gathered["fused"] = {"value": world * BATCH * g_steps / (float(f_ms.item()) * 1e-3), "unit": UNIT,
-                                 "collective": "lm_forward_gather: " + fg.mode, "matches_nccl_gather": f_ok}
-        except Exception as e:   # no peer access / symmetric memory on this box: NCCL figure stands alone
-            gathered["fused"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        dist.all_reduce(bad)
+    if int(bad.item()):
+        for f in failures:
+            print(f"bench.py: PARITY FAILURE on rank {rank}: {f}", file=sys.stderr, flush=True)
+        raise SystemExit(3)
 
     sampler.stop()
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
 
     if rank == 0:
-        peak, peak_src = measured_hbm_peak()
         algo_bytes = plan.bytes_per_clip * BATCH
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         cpu = cpu_baseline() if world == 1 else None

@@ -301,7 +301,10 @@ def test_forked_workers_decode_and_the_gpu_resamples_and_collates(tmp_path):
     for i, sr in enumerate(rates):
         xq = (np.rint(sigs[i] * 32767) / 32768.0).astype(np.float32)
         x16 = xq if sr == 16000 else O.resample(xq, sr, 16000).astype(np.float32)
-        assert np.abs(feats[i, 0] - O.logmel(x16, O.OracleConfig(duration=3.0))).max() < NORM_ATOL
+        # a resampled clip has almost no energy above the resampler's cut-off: there a 1e-6 waveform difference between
+        # the fp32 kernel and the float64 oracle resampler moves the dB value of an (empty) band visibly
+        tol = NORM_ATOL if sr == 16000 else 5e-3
+        assert np.abs(feats[i, 0] - O.logmel(x16, O.OracleConfig(duration=3.0))).max() < tol
 
 
 def test_transform_attributes_of_the_reference_class(golden):

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "audio_classification_icbhi_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "skew": ["-DLM_SKEW=1"],
+    "nofastnoise": ["-DLM_FASTNOISE=0"],
 }
 
 def build():
