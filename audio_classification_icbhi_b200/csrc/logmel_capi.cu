@@ -3,6 +3,7 @@
 // Host side only: plan construction (twiddles, banded filterbank rows), launch, and the
 // host-buffer pipeline.  No torch types, no ATen: plain pointers and sizes.
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -494,6 +495,10 @@ struct lm_resampler {
     int width = 0, ntaps = 0;
     float* d_taps = nullptr;
     int* d_k0 = nullptr;
+    // tiled kernel: taps padded to nt4 float4 per phase; shared memory for the widest input span of a 1024-output chunk
+    float4* d_taps4 = nullptr;
+    int nt4 = 0, k0max = 0;
+    size_t tile_smem = 0;     // 0 = the span does not fit: the untiled kernel is used
 };
 
 int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resampler** out) {
@@ -545,12 +550,29 @@ int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resa
     lm_resampler* r = new (std::nothrow) lm_resampler();
     if (!r) return LM_ERR_INVALID_ARG;
     r->device = device; r->orig = o; r->neu = q; r->width = width; r->ntaps = ntaps;
-    if (cudaMalloc(&r->d_taps, sizeof(float) * taps.size()) != cudaSuccess ||
+    r->nt4 = (ntaps + 3) / 4;
+    r->k0max = *std::max_element(k0.begin(), k0.end());
+    std::vector<float> taps4(static_cast<size_t>(q) * r->nt4 * 4, 0.0f);
+    for (int p = 0; p < q; ++p)
+        for (int i = 0; i < ntaps; ++i) taps4[(static_cast<size_t>(p) * r->nt4) * 4 + i] = taps[static_cast<size_t>(p) * ntaps + i];
+    {
+        const size_t span = static_cast<size_t>((lm::kRsChunk + q - 1) / q + 1) * o + r->k0max + 4 * r->nt4 + 8;
+        r->tile_smem = span * sizeof(float) <= 96 * 1024 ? span * sizeof(float) : 0;
+        if (const char* e = getenv("LM_RESAMPLE_UNTILED")) { if (e[0] == '1') r->tile_smem = 0; }   // tests compare the two kernels
+        if (r->tile_smem > 48 * 1024 &&
+            cudaFuncSetAttribute(lm::resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(r->tile_smem)) != cudaSuccess) {
+            cudaGetLastError();
+            r->tile_smem = 0;
+        }
+    }
+    if (cudaMalloc(&r->d_taps4, sizeof(float) * taps4.size()) != cudaSuccess ||
+        cudaMemcpy(r->d_taps4, taps4.data(), sizeof(float) * taps4.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc(&r->d_taps, sizeof(float) * taps.size()) != cudaSuccess ||
         cudaMalloc(&r->d_k0, sizeof(int) * q) != cudaSuccess ||
         cudaMemcpy(r->d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(r->d_k0, k0.data(), sizeof(int) * q, cudaMemcpyHostToDevice) != cudaSuccess) {
         const int rc = cuda_fail(cudaGetLastError(), "resampler tables");
-        cudaFree(r->d_taps); cudaFree(r->d_k0);
+        cudaFree(r->d_taps); cudaFree(r->d_k0); cudaFree(r->d_taps4);
         delete r;
         return rc;
     }
@@ -561,7 +583,7 @@ int lm_resampler_create(int32_t orig_freq, int32_t new_freq, int device, lm_resa
 int lm_resampler_destroy(lm_resampler* r) {
     if (!r) return LM_OK;
     cudaSetDevice(r->device);
-    cudaFree(r->d_taps); cudaFree(r->d_k0);
+    cudaFree(r->d_taps); cudaFree(r->d_k0); cudaFree(r->d_taps4);
     delete r;
     return LM_OK;
 }
@@ -581,7 +603,15 @@ int lm_resample_rows(const lm_resampler* r, const float* in, int64_t in_len, int
     const int threads = 256;
     const long long blocks = (n_out + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return LM_ERR_INVALID_ARG;
-    for (int32_t r0 = 0; r0 < n_rows; r0 += 65535) {   // grid.y limit
+    for (int32_t r0 = 0; r0 < n_rows && r->tile_smem; r0 += 65535) {   // tiled: one input span per 1024 outputs
+        const int32_t nr = std::min<int32_t>(65535, n_rows - r0);
+        const long long tblocks = (n_out + lm::kRsChunk - 1) / lm::kRsChunk;
+        lm::resample_tiled_kernel<<<dim3(static_cast<unsigned>(tblocks), static_cast<unsigned>(nr)), lm::kRsThreads, r->tile_smem,
+                                    static_cast<cudaStream_t>(cuda_stream)>>>(
+            in + static_cast<int64_t>(r0) * in_stride, in_len, in_stride, out + static_cast<int64_t>(r0) * out_stride, n_out,
+            out_stride, r->d_taps4, r->d_k0, r->orig, r->neu, r->nt4, r->width, r->k0max);
+    }
+    for (int32_t r0 = 0; r0 < n_rows && !r->tile_smem; r0 += 65535) {   // grid.y limit
         const int32_t nr = std::min<int32_t>(65535, n_rows - r0);
         lm::resample_kernel<<<dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(nr)), threads, 0,
                               static_cast<cudaStream_t>(cuda_stream)>>>(

@@ -233,11 +233,41 @@ class AudioPreprocessor:
                                            freq_mask_param=self.freq_mask_param,
                                            time_mask_param=self.time_mask_param)
 
+    def _pinned_stage(self, n: int) -> torch.Tensor:
+        """One of two grow-only pinned host buffers for packing a batch.  Each carries an event recorded after the copy
+        out of it (`_stage_release`); the buffer is reused only once that copy is done, so packing batch k+1 overlaps the
+        GPU work of batch k and never scribbles over a copy in flight."""
+        slots = self.__dict__.setdefault("_stages", [None, None])
+        self._stage_ix = 1 - getattr(self, "_stage_ix", 1)
+        slot = slots[self._stage_ix]
+        if slot is not None:
+            slot[1].synchronize()
+        if slot is None or slot[0].numel() < n:
+            slot = slots[self._stage_ix] = [torch.empty(max(n, 1 << 16), dtype=torch.float32).pin_memory(), torch.cuda.Event()]
+        return slot[0]
+
+    def _stage_release(self) -> None:
+        self._stages[self._stage_ix][1].record(torch.cuda.current_stream(self.plan.device))
+
+    @staticmethod
+    def _upload_noise(plan: LogMelPlan, aug, noise) -> Optional[torch.Tensor]:
+        """Host-drawn noise `[B, T]` -> device, moving only the rows of clips that drew noise (the kernel never reads
+        the row of a clip whose noise_scale is 0, so the rest of the device tensor stays uninitialised)."""
+        if noise is None:
+            return None
+        rows = np.nonzero(aug["noise_scale"] != 0)[0] if aug is not None else np.arange(noise.shape[0])
+        if len(rows) == noise.shape[0]:
+            return noise.to(plan.device, non_blocking=True)
+        noise_d = torch.empty(tuple(noise.shape), dtype=torch.float32, device=plan.device)
+        if len(rows):
+            ix = torch.from_numpy(rows)
+            noise_d.index_copy_(0, ix.to(plan.device), noise.index_select(0, ix).to(plan.device, non_blocking=True))
+        return noise_d
+
     def _finish(self, plan: LogMelPlan, wave, offset, length, aug, noise, B: int) -> torch.Tensor:
         """Runs the kernel(s).  Overridden by FlexibleAudioPreprocessor when a resize is needed."""
         aug_d = plan.upload_aug(aug) if aug is not None else None
-        noise_d = noise.to(plan.device, non_blocking=True) if noise is not None else None
-        return plan.forward(wave, offset, length, aug=aug_d, noise=noise_d)
+        return plan.forward(wave, offset, length, aug=aug_d, noise=self._upload_noise(plan, aug, noise))
 
     def preprocess_batch(self, waveforms: Union[Sequence[Wave], torch.Tensor],
                          lengths: Optional[Sequence[int]] = None, fast_augment: bool = False) -> torch.Tensor:
@@ -262,13 +292,25 @@ class AudioPreprocessor:
             for n in lens:           # 16-byte aligned clip starts: interior tiles go through TMA
                 starts.append(pos)
                 pos += (n + 3) & ~3
-            packed = torch.zeros(max(pos, 4), dtype=torch.float32, device=dev)
-            for s, c in zip(starts, clips):
-                if c.numel():
-                    packed[s:s + c.numel()].copy_(c, non_blocking=True)
+            packed = torch.empty(max(pos, 4), dtype=torch.float32, device=dev)   # alignment gaps are never read
+            # host clips: packed into ONE pinned staging buffer (kept on the object, grow-only) and sent with ONE
+            # asynchronous copy; clips that already live on the device (e.g. resampled by GpuCollate) are copied in place
+            host_ix = [i for i, c in enumerate(clips) if not c.is_cuda]
+            if host_ix:
+                lo, hi = starts[host_ix[0]], starts[host_ix[-1]] + lens[host_ix[-1]]
+                stage = self._pinned_stage(hi - lo)
+                for i in host_ix:
+                    if lens[i]:
+                        stage[starts[i] - lo:starts[i] - lo + lens[i]].copy_(clips[i])
+                if hi > lo:
+                    packed[lo:hi].copy_(stage[:hi - lo], non_blocking=True)
+                self._stage_release()
+            for i, c in enumerate(clips):        # after the block copy: it also covered their (stale) slots
+                if c.is_cuda and lens[i]:
+                    packed[starts[i]:starts[i] + lens[i]].copy_(c, non_blocking=True)
             wave = packed
-            offset = torch.tensor(starts, dtype=torch.int64, device=dev)
-            length = torch.tensor(lens, dtype=torch.int32, device=dev)
+            offset = torch.tensor(starts, dtype=torch.int64).to(dev, non_blocking=True)
+            length = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
         aug, noise = self._draw(B, fast_augment)
         return self._finish(plan, wave, offset, length, aug, noise, B)
 

@@ -84,6 +84,6 @@ class FlexibleAudioPreprocessor(AudioPreprocessor):
             wa = aug.copy()
             wa["f0"] = wa["f1"] = wa["t0"] = wa["t1"] = 0
             wave_aug_d = plan.upload_aug(wa)
-        noise_d = noise.to(plan.device, non_blocking=True) if noise is not None else None
+        noise_d = self._upload_noise(plan, aug, noise)
         db = plan.forward(wave, offset, length, aug=wave_aug_d, noise=noise_d, normalize=False)
         return self._resize_finish(db, fout, aug_d, normalize=True)

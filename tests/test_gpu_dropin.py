@@ -333,3 +333,16 @@ def test_transform_attributes_of_the_reference_class(golden):
     b = T.TimeMasking(time_mask_param=35)(T.FrequencyMasking(freq_mask_param=15)(spec))
     assert torch.equal(a, b)
     assert not hasattr(A.AudioPreprocessor(augment=False), "freq_mask")       # as in the reference: only with augment
+
+
+@pytest.mark.parametrize("sr", [44100, 4000, 10000, 22050, 48000])
+def test_tiled_resampler_is_bit_identical_to_the_plain_kernel(sr, monkeypatch):
+    """The shared-memory tiled resampler walks the same taps in the same order as the one-output-per-thread kernel."""
+    from audio_classification_icbhi_b200.resample import Resampler
+    x = torch.from_numpy(np.random.RandomState(sr).standard_normal((3, 2 * sr + 123)).astype(np.float32) * 0.1)
+    tiled = Resampler(sr, 16000)(x)
+    monkeypatch.setenv("LM_RESAMPLE_UNTILED", "1")
+    plain = Resampler(sr, 16000)(x)
+    assert tiled.shape == plain.shape and torch.equal(tiled, plain)
+    ref = O.resample(x[1].numpy(), sr, 16000)
+    assert np.abs(tiled[1].cpu().numpy() - ref).max() < 2e-6
