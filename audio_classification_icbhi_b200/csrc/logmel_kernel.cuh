@@ -227,8 +227,9 @@ __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __flo
 constexpr float kStatScaleS = 16777216.0f, kStatScaleQ = 65536.0f;
 __device__ __forceinline__ void stat_add(longlong2* __restrict__ slot, float ssum, float qsum) {
     longlong2 st = *slot;
-    st.x += __float2ll_rn(ssum * kStatScaleS);
-    st.y += __float2ll_rn(qsum * kStatScaleQ);
+    // through fp64: a three-instruction conversion (the fp32 -> int64 intrinsic expands to a dozen), exact scaling
+    st.x += __double2ll_rn(static_cast<double>(ssum) * static_cast<double>(kStatScaleS));
+    st.y += __double2ll_rn(static_cast<double>(qsum) * static_cast<double>(kStatScaleQ));
     *slot = st;
 }
 

@@ -568,13 +568,14 @@ def run_b200(args) -> None:
     peak, peak_src = measured_hbm_peak()
     extra = {}
     failures = []
-    extra["strong_scaling"] = strong_scaling(plan, clips, world, rank, dev, peak, failures)
-    extra["ragged_corpus"] = corpus_config(plan, world, rank, dev, peak, failures)
-    extra["analyzer_windows"] = windows_config(world, rank, dev, peak, failures)
-    if rank == 0:
-        extra["latency_single_clip_us"] = latency_config(plan, dev)
-        extra["train_batch"] = train_batch_config(dev, peak)
-    gathered = gathered_headline(plan, wave, offset, length, out, world, dev, args, failures) if world > 1 else None
+    if not args.headline_only:
+        extra["strong_scaling"] = strong_scaling(plan, clips, world, rank, dev, peak, failures)
+        extra["ragged_corpus"] = corpus_config(plan, world, rank, dev, peak, failures)
+        extra["analyzer_windows"] = windows_config(world, rank, dev, peak, failures)
+        if rank == 0:
+            extra["latency_single_clip_us"] = latency_config(plan, dev)
+            extra["train_batch"] = train_batch_config(dev, peak)
+    gathered = gathered_headline(plan, wave, offset, length, out, world, dev, args, failures) if (world > 1 and not args.headline_only) else None
     bad = torch.tensor([len(failures)], device=dev)
     if world > 1:
         dist.all_reduce(bad)
@@ -590,7 +591,7 @@ def run_b200(args) -> None:
     if rank == 0:
         algo_bytes = plan.bytes_per_clip * BATCH
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-        cpu = cpu_baseline() if world == 1 else None
+        cpu = cpu_baseline() if (world == 1 and not args.headline_only) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -635,6 +636,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the other BASELINE configs and the CPU baseline (short runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
