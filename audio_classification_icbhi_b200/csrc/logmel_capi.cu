@@ -326,6 +326,18 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
             load_w[best] += tab.ndk[mt] + 4;      // a tile's fixed cost (setup + epilogue) is worth ~4 steps
             load_s[best & 3] += tab.ndk[mt] + 4;
         }
+        // tensor-memory columns of the tiles' fragments: a warp reads only its own lane quadrant (warp % 4), so the
+        // tiles of warps q and q + 4 share quadrant q, 8 columns per 16-bin step
+        int col_q[4] = {lm::kTmFb, lm::kTmFb, lm::kTmFb, lm::kTmFb};
+        for (int& c : tab.tcol) c = lm::kTmFb;
+        for (int w = 0; w < lm::kGroupWarps; ++w)
+            for (int sl = 0; sl < cnt_w[w]; ++sl) {
+                const int mt = tab.warp_tile[w][sl];
+                tab.tcol[mt] = col_q[w & 3];
+                col_q[w & 3] += 8 * tab.ndk[mt];
+            }
+        for (int q = 0; q < 4; ++q)
+            if (LM_TM_FB && col_q[q] > lm::kTmCols) { free_plan(p); return LM_ERR_FILTERBANK; }
     }
 
     // ---- twiddles ---------------------------------------------------------------------------

@@ -71,6 +71,25 @@
 #ifndef LM_TW2
 #define LM_TW2 1   // 1: twiddle = product of two table entries (10 table rows); 0: full table (31 rows, 8 KB)
 #endif
+// Tensor memory as the kernel's constant-operand store.  The tables that never change -- the mel A fragments
+// (84 KB), the window, the FFT twiddles and the untangle twiddles -- are ~150 of the ~520 shared-memory wavefronts a
+// frame costs, on the busiest pipe of the kernel (72 %).  TMEM (256 KB per SM, read with tcgen05.ld at > 3 KB/clk,
+// not through the LSU data pipe) holds them instead: every warp reads its own lane quadrant, so the tables that
+// all warps need are replicated in the four quadrants and a mel tile's fragments live in the quadrant of the warp
+// that owns the tile.  LM_TM_* = 0 falls back to shared memory for that table (experiments).
+#ifndef LM_TM_FB
+#define LM_TM_FB 0
+#endif
+#ifndef LM_TM_WIN
+#define LM_TM_WIN 0
+#endif
+#ifndef LM_TM_TW
+#define LM_TM_TW 0
+#endif
+#ifndef LM_TM_UTW
+#define LM_TM_UTW 0
+#endif
+#define LM_TMEM (LM_TM_FB || LM_TM_WIN || LM_TM_TW || LM_TM_UTW)
 #if LM_TIMING
 #define LM_T(slot) do { const long long t_now_ = clock64(); t_acc[slot] += t_now_ - t_last; t_last = t_now_; } while (0)
 #else
@@ -101,7 +120,15 @@ struct MelTable {                             // lives in global memory, copied 
     int ndk[kMaxMelTiles];                    // 16-bin steps in the band
     int off[kMaxMelTiles];                    // first step's index into melw (units of 64 float4)
     int warp_tile[kGroupWarps][kTileSlots];   // mel tiles owned by each warp of a group (-1 = none)
+    int tcol[kMaxMelTiles];                   // first TMEM column of the tile's fragments (8 columns per 16-bin step),
+                                              // in the lane quadrant (warp % 4) of the warp that owns the tile
 };
+// TMEM column map (every lane quadrant): window, FFT twiddles (31 x (cos, -sin)), untangle twiddles, mel fragments
+constexpr int kTmWin = 0;      // 32 columns: lane l, column 2r + j = window[64 r + 2 l + j]   (n_fft 1024: column r = window[32 r + l])
+constexpr int kTmTw = 32;      // 64 columns: column 2 (k1 - 1) + j = (cos, -sin)(2 pi l k1 / 1024)[j], k1 = 1 .. 31
+constexpr int kTmUtw = 96;     // 16 columns: column 2 i + j = (cos, sin)(2 pi (l + 32 i) / 2048)[j]
+constexpr int kTmFb = 112;     // mel A fragments up to column 512
+constexpr int kTmCols = 512;
 
 struct KParams {
     // batch
@@ -192,6 +219,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void group_bar(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
 }
+// ---- tensor memory (tcgen05): allocation by one warp, 32x32b loads / stores (lane = TMEM lane, register = column) ----
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sttm8(uint32_t taddr, const float (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(r[0]), "f"(r[1]),
+                 "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void sttm_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// The load is asynchronous: its registers are valid after ldtm_wait8 on the same array.  No memory clobber: TMEM is
+// written once, before the CTA-wide barrier; the dependence on the wait is carried by the "+f" operands, so the
+// compiler stays free to move shared-memory traffic across both.
+__device__ __forceinline__ void ldtm8(float (&r)[8], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void ldtm_wait8(float (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]));
+}
 // D += A(16x8, row) * B(8x8, col), TF32 inputs (low 13 mantissa bits ignored), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -265,12 +320,31 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t idx) {
 //           separately; the LDS.128 reads hand the second FFT register pairs of neighbouring
 //           points, the layout its packed stages 1-4 want -- see gen_fft.py) + second radix-32 FFT.
 // ---------------------------------------------------------------------------------------
-#if LM_TW2
+#if LM_TW2 && !LM_TM_TW
 constexpr int kTwRows = 10;   // twiddle table rows kept on chip: k1 = 1, 2, 3, 4, 8, 12, ..., 28
 #else
 constexpr int kTwRows = 31;   // k1 = 1 .. 31
 #endif
-__device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane) {
+__device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __restrict__ tw, int lane, uint32_t tq) {
+#if LM_TM_TW
+    // all 31 twiddles of this lane straight from tensor memory, four at a time, the next four in flight
+    float wv[2][8];
+    ldtm8(wv[0], tq + kTmTw);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        ldtm_wait8(wv[c & 1]);
+        if (c < 7) ldtm8(wv[(c + 1) & 1], tq + kTmTw + 8 * (c + 1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k1 = 4 * c + j + 1;
+            if (k1 < 32) {
+                const float wx = wv[c & 1][2 * j], wy = wv[c & 1][2 * j + 1];   // (cos, -sin): (r + i m)(wx + i wy) = (r wx - m wy, m wx + r wy)
+                z[k1] = lm_fma2(lm_swap(z[k1]), lm_pack(-wy, wy), lm_mul2(z[k1], lm_bcast(wx)));
+            }
+        }
+    }
+    return;
+#endif
 #if !LM_TW2
 #pragma unroll
     for (int k1 = 1; k1 < 32; ++k1) {
@@ -305,8 +379,8 @@ __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __res
 }
 __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
                                                     float* __restrict__ scr, const float2* __restrict__ tw, int lane,
-                                                    bool do_twiddle = true) {
-    if (do_twiddle) warp_twiddle(z, tw, lane);
+                                                    uint32_t tq, bool do_twiddle = true) {
+    if (do_twiddle) warp_twiddle(z, tw, lane, tq);
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -375,21 +449,21 @@ struct Geo {
 // the run-time sized arrays (staging buffers, filterbank) sit at the end.
 template <int NFFT>
 struct Smem {
-    static constexpr size_t kBar = 0;                                    // kGroups mbarriers + 'TMA pending' flags
+    static constexpr size_t kBar = 0;                                    // kGroups mbarriers + 'TMA pending' flags; +40: TMEM base address
     static constexpr size_t kRed = kBar + 48;                            // + the filterbank-copy mbarrier at +32                            // per group: reduction scratch + broadcast
     static constexpr size_t kRedGroup = sizeof(long long) * 2 * kGroupWarps + 16;   // + bcast[3]: mean, std + eps, 'this group normalises'
     static constexpr size_t kCtx = kRed + kGroups * kRedGroup;           // per group two ClipCtx slots (ordinal & 1)
     static constexpr size_t kTab = kCtx + kGroups * 2 * 80;
     static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fixed-point (sum, sumsq)
     static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
-    static constexpr size_t kTw = kWin + sizeof(float) * (NFFT / 2);     // first half of the window
-    static constexpr size_t kUtw = kTw + sizeof(float2) * 32 * kTwRows;
-    static constexpr size_t kScr = kUtw + ((NFFT == 2048) ? sizeof(float2) * 512 : 0);
+    static constexpr size_t kTw = kWin + (LM_TM_WIN ? 0 : sizeof(float) * (NFFT / 2));     // first half of the window
+    static constexpr size_t kUtw = kTw + (LM_TM_TW ? 0 : sizeof(float2) * 32 * kTwRows);
+    static constexpr size_t kScr = kUtw + ((NFFT == 2048 && !LM_TM_UTW) ? sizeof(float2) * 512 : 0);
     static constexpr size_t kSbuf = kScr + sizeof(float) * kWarps * kRowFloats;
     static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0 && kRedGroup % 16 == 0, "alignment");
     static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * kGroups * static_cast<size_t>(ns); }
     static __host__ __device__ size_t total(int ns, int n_dk) {
-        return melw_offset(ns) + sizeof(float4) * 64 * static_cast<size_t>(n_dk);
+        return melw_offset(ns) + (LM_TM_FB ? 0 : sizeof(float4) * 64 * static_cast<size_t>(n_dk));
     }
 };
 
@@ -512,11 +586,74 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     float* const sb = reinterpret_cast<float*>(smem_raw + L::kSbuf) + static_cast<size_t>(group) * p.ns;
     float4* const s_melw = reinterpret_cast<float4*>(smem_raw + L::melw_offset(p.ns));
 
-    // ---- constants -> shared memory, once per (persistent) CTA, by all 16 warps -----------------
+    // ---- constants -> tensor memory / shared memory, once per (persistent) CTA -----------------
+#if LM_TMEM
+    uint32_t* const s_tmem = reinterpret_cast<uint32_t*>(smem_raw + L::kBar + 40);
+    if (tid < 32) tmem_alloc(smem_u32(s_tmem), kTmCols);   // the CTA is alone on its SM (shared memory): all 512 columns
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tq = *s_tmem + (static_cast<uint32_t>((tid >> 5) & 3) << 21);   // this warp's lane quadrant: TMEM lanes 32 (warp % 4) ...
+    if (tid < 128) {   // warps 0-3, one per quadrant: the tables every warp reads
+        float v[8];
+        if (LM_TM_WIN) {
+            for (int c = 0; c < (NFFT == 2048 ? 32 : 16); c += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (NFFT == 2048) ? p.window[64 * ((c + j) >> 1) + 2 * lane_ + ((c + j) & 1)] : p.window[32 * (c + j) + lane_];
+                sttm8(tq + kTmWin + c, v);
+            }
+        }
+        if (LM_TM_TW) {
+            for (int c = 0; c < 64; c += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (c + j) >> 1;   // k1 - 1
+                    const float2 w = p.tw[(r < 31 ? r : 30) * 32 + lane_];
+                    v[j] = ((c + j) & 1) ? w.y : w.x;
+                }
+                sttm8(tq + kTmTw + c, v);
+            }
+        }
+        if (LM_TM_UTW && NFFT == 2048) {
+            for (int c = 0; c < 16; c += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 w = p.utw[lane_ + 32 * ((c + j) >> 1)];
+                    v[j] = ((c + j) & 1) ? w.y : w.x;
+                }
+                sttm8(tq + kTmUtw + c, v);
+            }
+        }
+    }
+    if (LM_TM_FB && tid < kGroupThreads) {   // warps 0-7 = the eight tile owners of a group (both groups read the same fragments)
+        for (int slot = 0; slot < kTileSlots; ++slot) {
+            const int mt = p.mel_table->warp_tile[tid >> 5][slot];
+            if (mt < 0) break;
+            const int ndk = p.mel_table->ndk[mt];
+            const float4* __restrict__ src = p.melw + static_cast<size_t>(p.mel_table->off[mt]) * 64 + lane_;
+            const uint32_t col = tq + static_cast<uint32_t>(p.mel_table->tcol[mt]);
+            for (int d = 0; d < ndk; ++d) {
+                const float4 w1 = src[64 * d], w2 = src[64 * d + 32];
+                const float v[8] = {w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+                sttm8(col + 8 * d, v);
+            }
+        }
+    }
+    sttm_wait();
+    tc_fence_before();   // pairs with the fence after the CTA-wide barrier below
+#endif
+#if !LM_TM_WIN
     for (int i = tid; i < HALF; i += kThreads) s_win[i] = p.window[i];
+#endif
+#if !LM_TM_TW
     for (int i = tid; i < 32 * kTwRows; i += kThreads) s_tw[i] = p.tw[i];
+#endif
+#if !LM_TM_UTW
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
+#endif
+#if !LM_TM_FB
     // the banded filterbank (up to 96 KB) is needed first in the mel phase of the first item: one bulk copy, in flight
     // during the first FFT, completing on its own mbarrier (every thread waits for it once, before its first mel phase)
     uint64_t* const mbar_fb = reinterpret_cast<uint64_t*>(smem_raw + L::kBar + 32);
@@ -526,6 +663,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         mbar_expect_tx(mbar_fb, static_cast<uint32_t>(p.n_dk) * 1024u);
         bulk_g2s(s_melw, p.melw, static_cast<uint32_t>(p.n_dk) * 1024u, mbar_fb);
     }
+#endif
+#if !LM_TMEM
+    const uint32_t tq = 0;
+#endif
     for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
         reinterpret_cast<int*>(smem_raw + L::kTab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
     for (int i = gtid; i < kGroupWarps * kRowFloats; i += kGroupThreads) rows[i] = 0.0f;   // pad columns stay finite
@@ -535,13 +676,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         fence_mbar_init();
         *s_pend = 0;
     }
-    __syncthreads();   // the only CTA-wide barrier: from here on the groups never meet again
+    __syncthreads();   // from here on the groups never meet again (until the CTA's end, where warp 0 frees the tensor memory)
+#if LM_TMEM
+    tc_fence_after();
+#endif
 
     // ---- this group's clips -----------------------------------------------------------------------
     const int nv = static_cast<int>(gridDim.x) * kGroups;
     const int n_virtual = p.B * p.split;
     const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);   // first (virtual) clip: static
-    if (clip0 >= n_virtual) return;
+    if (clip0 < n_virtual) {   // an idle group goes straight to the CTA's end
 
     const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
     const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
@@ -630,7 +774,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     }
 
     uint32_t parity = 0;                   // mbarrier phase of the staging buffer (group-uniform)
+#if !LM_TM_FB
     bool fb_ready = false;                 // this thread has seen the filterbank copy complete
+#endif
     s_stat[tid] = make_longlong2(0, 0);    // this thread's running (sum, sum of squares) of the clip's dB values, fixed point
     int tile = s_ctx[0].t_begin, t_end = s_ctx[0].t_end, ord = 0, clip = s_ctx[0].clip;   // tile, end of the tile range, clip ordinal (context slot = ord & 1), clip index
 
@@ -704,6 +850,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             const int lane = launder(lane_), gw = launder(gwarp_);
             if (NFFT == 2048) {
                 const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + gw * hop);
+#if LM_TM_WIN
+                float wv[2][8];   // the lane's 32 window values, four pairs at a time, the next four in flight
+                ldtm8(wv[0], tq + kTmWin);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ldtm_wait8(wv[c & 1]);
+                    if (c < 3) ldtm8(wv[(c + 1) & 1], tq + kTmWin + 8 * (c + 1));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * c + j;
+                        const float2 v1 = s2[32 * r + lane];
+                        const float2 v2 = s2[32 * (r + 16) + lane];
+                        const lm_f2 V1 = lm_pack(v1.x, v1.y), V2 = lm_pack(v2.x, v2.y), W = lm_pack(wv[c & 1][2 * j], wv[c & 1][2 * j + 1]);
+                        z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
+                        z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-v2.x, -v2.y));
+                    }
+                }
+#else
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
@@ -714,21 +878,34 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
                     z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-v2.x, -v2.y));
                 }
+#endif
             } else {
                 // n_fft = 1024: two frames per warp as one complex signal z = a + i b
                 const float* __restrict__ sa = sb + (2 * gw) * hop;
                 const float* __restrict__ sbb = sa + hop;
+#if LM_TM_WIN
+                float wv[2][8];
+                ldtm8(wv[0], tq + kTmWin);
+                ldtm8(wv[1], tq + kTmWin + 8);
+                ldtm_wait8(wv[0]);
+                ldtm_wait8(wv[1]);
+#endif
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const float a1 = sa[32 * r + lane], a2 = sa[32 * (r + 16) + lane];
                     const float b1 = sbb[32 * r + lane], b2 = sbb[32 * (r + 16) + lane];
-                    const lm_f2 V1 = lm_pack(a1, b1), V2 = lm_pack(a2, b2), W = lm_bcast(s_win[32 * r + lane]);
+#if LM_TM_WIN
+                    const lm_f2 W = lm_bcast(wv[r >> 3][r & 7]);
+#else
+                    const lm_f2 W = lm_bcast(s_win[32 * r + lane]);
+#endif
+                    const lm_f2 V1 = lm_pack(a1, b1), V2 = lm_pack(a2, b2);
                     z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
                     z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-a2, -b2));
                 }
             }
             lm_fft32_aos_from2(z);
-            if (LM_SKEW && (gw & 1)) warp_twiddle(z, s_tw, lane);
+            if (LM_SKEW && (gw & 1)) warp_twiddle(z, s_tw, lane, tq);
         }
         LM_T(1);   // FFT part 1
         group_bar(group);   // (A) every warp of the group is done with the mel phase of the previous item
@@ -748,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             const int lane = launder(lane_), gw = launder(gwarp_);
             float* const scr = rows + gw * kRowFloats;
             float xr[32], xi[32];
-            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane, !(LM_SKEW && (gw & 1)));
+            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane, tq, !(LM_SKEW && (gw & 1)));
             const int srcl = (32 - lane) & 31;
             const bool l0 = (lane == 0);
             if (NFFT == 2048) {
@@ -758,6 +935,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 // partners are the other lane's slots 31-i and 15-i, and the hi twiddle is the lo one
                 // turned by pi/2: (c, s)(k+512) = (-s, c)(k).  The row was last read inside part 2
                 // (followed by __syncwarp): 4|X|^2 goes straight into it, bin-major.
+#if LM_TM_UTW
+                float uv[2][8];
+                ldtm8(uv[0], tq + kTmUtw);
+                ldtm8(uv[1], tq + kTmUtw + 8);
+                ldtm_wait8(uv[0]);
+                ldtm_wait8(uv[1]);
+#endif
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float s_lr = l0 ? xr[(32 - i) & 31] : xr[31 - i];
@@ -771,7 +955,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     const lm_f2 Ar = lm_pack(xr[i], xr[i + 16]), Ai = lm_pack(xi[i], xi[i + 16]);
                     const lm_f2 Br = lm_pack(b_lr, b_hr), Bi = lm_pack(b_li, b_hi);
                     const lm_f2 Er = lm_add2(Ar, Br), Ei = lm_sub2(Ai, Bi), Or = lm_add2(Ai, Bi), Oi = lm_sub2(Br, Ar);
+#if LM_TM_UTW
+                    const float2 cs = make_float2(uv[i >> 2][2 * (i & 3)], uv[i >> 2][2 * (i & 3) + 1]);
+#else
                     const float2 cs = s_utw[lane + 32 * i];
+#endif
                     const lm_f2 C = lm_pack(cs.x, -cs.y), S = lm_pack(cs.y, cs.x), nS = lm_pack(-cs.y, -cs.x);
                     const lm_f2 Tr = lm_fma2(C, Or, lm_mul2(S, Oi));
                     const lm_f2 Ti = lm_fma2(C, Oi, lm_mul2(nS, Or));
@@ -819,7 +1007,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         LM_T(4);   // barrier B
 
         // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
+#if !LM_TM_FB
         if (!fb_ready) { mbar_wait(mbar_fb, 0); fb_ready = true; }
+#endif
         {
             const int lane = launder(lane_), gw = launder(gwarp_);
             const int g = lane >> 2, tg = lane & 3;
@@ -835,7 +1025,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 const int mt = s_tab->warp_tile[gw][slot];
                 if (mt < 0 || LM_EXP == 1) break;
                 const int kb = s_tab->kb[mt], ndk = s_tab->ndk[mt];
+#if LM_TM_FB
+                const uint32_t tcol = tq + static_cast<uint32_t>(s_tab->tcol[mt]);
+                float wa[8], wb[8];                       // the A fragments of steps d and d + 1 (one in use, one in flight)
+                ldtm8(wa, tcol);
+#else
                 const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 64 + lane;
+#endif
                 // B operand: frame n = g of column block nb lives in warp row (8 nb + g) / FPW
                 // (+ kPbOff for the odd frame); this lane reads bins kb + 16 d + 4 tg .. +3 of it
                 const float* rp[G::NB];
@@ -847,11 +1043,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { acc_h[nb][q] = 0.f; acc_l[nb][q] = 0.f; }
                 }
-#pragma unroll 2
-                for (int d = 0; d < ndk; ++d) {
-                    // A operand rows 0-7: TF32 head of fb[., mel g], rows 8-15: its residual; one LDS.128 is one
-                    // k-step's fragment.  k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
-                    const float4 w1 = wp[64 * d], w2 = wp[64 * d + 32];
+                // A operand rows 0-7: TF32 head of fb[., mel g], rows 8-15: its residual; one float4 is one k-step's
+                // fragment.  k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
+                auto mel_step = [&](const float4 w1, const float4 w2, int d) {
 #pragma unroll
                     for (int nb = 0; nb < G::NB; ++nb) {
                         const float4 pv = *reinterpret_cast<const float4*>(rp[nb] + 16 * d);
@@ -865,7 +1059,25 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                         mma_tf32(acc_l[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w),
                                  __float_as_uint(lm_lo(r23)), __float_as_uint(lm_hi(r23)));
                     }
+                };
+#if LM_TM_FB
+                // the fragments come from tensor memory (8 columns per step), the next step's load in flight during the MMAs
+#pragma unroll 1
+                for (int d = 0; d < ndk; d += 2) {
+                    ldtm_wait8(wa);
+                    if (d + 1 < ndk) ldtm8(wb, tcol + 8 * (d + 1));
+                    mel_step(make_float4(wa[0], wa[1], wa[2], wa[3]), make_float4(wa[4], wa[5], wa[6], wa[7]), d);
+                    if (d + 1 < ndk) {
+                        ldtm_wait8(wb);
+                        if (d + 2 < ndk) ldtm8(wa, tcol + 8 * (d + 2));
+                        mel_step(make_float4(wb[0], wb[1], wb[2], wb[3]), make_float4(wb[4], wb[5], wb[6], wb[7]), d + 1);
+                    }
                 }
+                if (ndk == 0) ldtm_wait8(wa);   // never leave a load in flight
+#else
+#pragma unroll 2
+                for (int d = 0; d < ndk; ++d) mel_step(wp[64 * d], wp[64 * d + 32], d);
+#endif
                 // epilogue: c0:(head row, frame 2tg) c1:(head, 2tg+1) c2:(residual row, 2tg) c3:(residual, 2tg+1)
                 const int m = mt * 8 + g;
                 const bool ok_m = m < n_mels;
@@ -995,7 +1207,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
         }
         LM_T(7);   // normalisation
     }
+#if !LM_TM_FB
     if (!fb_ready) mbar_wait(mbar_fb, 0);   // (all tiles silent) never leave a bulk copy in flight behind an exiting CTA
+#endif
     // the last group to finish leaves the launch's counters at zero for the next launch that uses this slot
     if (gtid == 0) {
         const int active = n_virtual < nv ? n_virtual : nv;
@@ -1011,6 +1225,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = t_acc[i];
     }
+#endif
+    }   // active group
+#if LM_TMEM
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(*s_tmem, kTmCols);
 #endif
 }
 

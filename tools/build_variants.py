@@ -9,8 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "audio_classification_icbhi_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "variants")
 VARIANTS = {
-    "nofastnoise": ["-DLM_FASTNOISE=0"],
+    "fftonly": ["-DLM_EXP=1"],
+    "melonly": ["-DLM_EXP=2"],
 }
+if len(sys.argv) > 2:   # python tools/build_variants.py build name=-DFLAG,-DFLAG ...
+    VARIANTS = {a.split("=", 1)[0]: a.split("=", 1)[1].split(",") for a in sys.argv[2:]}
 
 def build():
     os.makedirs(OUT, exist_ok=True)

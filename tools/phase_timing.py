@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from audio_classification_icbhi_b200 import _lib
-_lib.LIB_PATH = os.path.join(ROOT, "tools", "variants", "liblogmel_timing.bin")
+_lib.LIB_PATH = os.path.join(ROOT, "tools", "variants", f"liblogmel_{os.environ.get('LM_VARIANT', 'timing')}.bin")
 from audio_classification_icbhi_b200.plan import LogMelPlan
 plan = LogMelPlan(device="cuda:0")
 B, T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 80000
