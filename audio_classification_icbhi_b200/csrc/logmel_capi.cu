@@ -78,7 +78,7 @@ struct lm_plan {
     int device = 0;
     int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
     int tile_f = 0, n_tiles = 0, ns = 0, n_dk = 0, fb_nnz = 0;
-    int sm_count = 0, max_ctas = 0, use_tma = 1, stagger_ns = 0;
+    int sm_count = 0, max_ctas = 0, use_tma = 1;
     int host_chunk_clips = 0;   // lm_forward_host chunk size; 0 = automatic
     size_t smem_bytes = 0;
     float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
@@ -118,7 +118,7 @@ int free_plan(lm_plan* p) {
 lm::KParams make_params(const lm_plan* p) {
     lm::KParams k{};
     k.T = p->T; k.hop = p->hop; k.frames = p->frames; k.n_mels = p->n_mels; k.n_tiles = p->n_tiles;
-    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma; k.stagger_ns = p->stagger_ns;
+    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma;
     k.db_scale = static_cast<float>(static_cast<double>(p->db_mult) * 0.30102999566398119521);
     k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
     k.norm_eps = p->norm_eps;
@@ -140,8 +140,8 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     const long long seq = p->launches.fetch_add(1);
     k.work_counter = p->d_counters + 2 * (seq % kCounters);   // zero now, left at zero by the kernel (no memset per launch)
     const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
-    // Small batches: fewer clips than 8-warp groups on the GPU.  Cut every clip into chunks of whole tiles so that
-    // (almost) every group gets one chunk; statistics are combined with integer atomics (logmel_kernel.cuh).
+    // Small batches: fewer clips than CTAs on the GPU.  Cut every clip into chunks of whole tiles so that
+    // (almost) every CTA gets one chunk; statistics are combined with integer atomics (logmel_kernel.cuh).
     k.split = 1; k.tiles_per_chunk = p->n_tiles;
     const int groups = cap * lm::kGroups;
     if (normalize && p->split_override != 1 && B < groups && B <= kMaxSplitClips && p->n_tiles > 1) {
@@ -326,18 +326,6 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
             load_w[best] += tab.ndk[mt] + 4;      // a tile's fixed cost (setup + epilogue) is worth ~4 steps
             load_s[best & 3] += tab.ndk[mt] + 4;
         }
-        // tensor-memory columns of the tiles' fragments: a warp reads only its own lane quadrant (warp % 4), so the
-        // tiles of warps q and q + 4 share quadrant q, 8 columns per 16-bin step
-        int col_q[4] = {lm::kTmFb, lm::kTmFb, lm::kTmFb, lm::kTmFb};
-        for (int& c : tab.tcol) c = lm::kTmFb;
-        for (int w = 0; w < lm::kGroupWarps; ++w)
-            for (int sl = 0; sl < cnt_w[w]; ++sl) {
-                const int mt = tab.warp_tile[w][sl];
-                tab.tcol[mt] = col_q[w & 3];
-                col_q[w & 3] += 8 * tab.ndk[mt];
-            }
-        for (int q = 0; q < 4; ++q)
-            if (LM_TM_FB && col_q[q] > lm::kTmCols) { free_plan(p); return LM_ERR_FILTERBANK; }
     }
 
     // ---- twiddles ---------------------------------------------------------------------------
@@ -412,6 +400,10 @@ int lm_debug_timing(long long* host_out, int n) {
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host_out, lm::g_timing, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
 }
+int lm_debug_trace(long long* host_out, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_out, lm::g_trace, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
+}
 #endif
 
 int lm_plan_frames(const lm_plan* plan) { return plan ? plan->frames : LM_ERR_INVALID_ARG; }
@@ -434,7 +426,6 @@ int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!plan || !key) return LM_ERR_INVALID_ARG;
     if (!strcmp(key, "tma")) { plan->use_tma = value ? 1 : 0; return LM_OK; }
     if (!strcmp(key, "host_chunk_clips")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->host_chunk_clips = value; return LM_OK; }
-    if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
     if (!strcmp(key, "split")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->split_override = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
