@@ -78,7 +78,7 @@ struct lm_plan {
     int device = 0;
     int n_fft = 0, hop = 0, n_mels = 0, T = 0, frames = 0, n_freqs = 0;
     int tile_f = 0, n_tiles = 0, ns = 0, n_dk = 0, fb_nnz = 0;
-    int sm_count = 0, max_ctas = 0, use_tma = 1;
+    int sm_count = 0, max_ctas = 0, use_tma = 1, stagger_ns = 0;
     int host_chunk_clips = 0;   // lm_forward_host chunk size; 0 = automatic
     size_t smem_bytes = 0;
     float db_mult = 10.f, amin = 1e-10f, db_offset = 0.f, floor_db = -100.f, norm_eps = 1e-8f;
@@ -118,7 +118,7 @@ int free_plan(lm_plan* p) {
 lm::KParams make_params(const lm_plan* p) {
     lm::KParams k{};
     k.T = p->T; k.hop = p->hop; k.frames = p->frames; k.n_mels = p->n_mels; k.n_tiles = p->n_tiles;
-    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma;
+    k.ns = p->ns; k.n_dk = p->n_dk; k.use_tma = p->use_tma; k.stagger_ns = p->stagger_ns;
     k.db_scale = static_cast<float>(static_cast<double>(p->db_mult) * 0.30102999566398119521);
     k.amin = p->amin; k.db_offset = p->db_offset; k.floor_db = p->floor_db;
     k.norm_eps = p->norm_eps;
@@ -129,7 +129,7 @@ lm::KParams make_params(const lm_plan* p) {
 int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* length, int32_t B,
            const lm_aug* aug, const float* noise, float* out_norm, float* out_db, float* out_melpow,
            int32_t normalize, cudaStream_t stream, float* const* peers = nullptr, int n_peers = 0,
-           float* mc_out = nullptr) {
+           float* mc_out = nullptr, bool pcm16 = false) {
     if (B == 0) return LM_OK;
     lm::KParams k = make_params(p);
     for (int r = 0; r < n_peers; ++r) k.peer[r] = peers[r];
@@ -140,8 +140,8 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     const long long seq = p->launches.fetch_add(1);
     k.work_counter = p->d_counters + 2 * (seq % kCounters);   // zero now, left at zero by the kernel (no memset per launch)
     const int cap = p->max_ctas > 0 ? p->max_ctas : p->sm_count;
-    // Small batches: fewer clips than CTAs on the GPU.  Cut every clip into chunks of whole tiles so that
-    // (almost) every CTA gets one chunk; statistics are combined with integer atomics (logmel_kernel.cuh).
+    // Small batches: fewer clips than 8-warp groups on the GPU.  Cut every clip into chunks of whole tiles so that
+    // (almost) every group gets one chunk; statistics are combined with integer atomics (logmel_kernel.cuh).
     k.split = 1; k.tiles_per_chunk = p->n_tiles;
     const int groups = cap * lm::kGroups;
     if (normalize && p->split_override != 1 && B < groups && B <= kMaxSplitClips && p->n_tiles > 1) {
@@ -166,7 +166,11 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
     const int grid = std::min<int>(B * k.split, cap);
     const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
     const bool device_noise = (aug != nullptr) && (noise == nullptr);   // clips may ask for Philox noise drawn in the kernel
-    if (p->n_fft == 2048) {
+    if (pcm16) {   // `wave` holds 16-bit samples (lm_forward_pcm16): expanded inside the staging, no decode kernel
+        if (extra) return LM_ERR_UNSUPPORTED;
+        if (p->n_fft == 2048) lm::logmel_kernel<2048, false, false, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+        else lm::logmel_kernel<1024, false, false, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
+    } else if (p->n_fft == 2048) {
         if (extra) lm::logmel_kernel<2048, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
         else if (device_noise) lm::logmel_kernel<2048, false, true><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
         else lm::logmel_kernel<2048, false><<<grid, lm::kThreads, p->smem_bytes, stream>>>(k);
@@ -379,12 +383,18 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(lm::logmel_kernel<2048, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(p->smem_bytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm::logmel_kernel<2048, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(p->smem_bytes));
     } else {
         p->smem_bytes = lm::Smem<1024>::total(p->ns, p->n_dk);
         e = cudaFuncSetAttribute(lm::logmel_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(p->smem_bytes));
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(lm::logmel_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(p->smem_bytes));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(lm::logmel_kernel<1024, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(p->smem_bytes));
     }
     if (e != cudaSuccess) { free_plan(p); return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
@@ -399,10 +409,6 @@ int lm_plan_destroy(lm_plan* plan) { return free_plan(plan); }
 int lm_debug_timing(long long* host_out, int n) {
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host_out, lm::g_timing, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
-}
-int lm_debug_trace(long long* host_out, int n) {
-    cudaDeviceSynchronize();
-    return cudaMemcpyFromSymbol(host_out, lm::g_trace, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
 }
 #endif
 
@@ -426,6 +432,7 @@ int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!plan || !key) return LM_ERR_INVALID_ARG;
     if (!strcmp(key, "tma")) { plan->use_tma = value ? 1 : 0; return LM_OK; }
     if (!strcmp(key, "host_chunk_clips")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->host_chunk_clips = value; return LM_OK; }
+    if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
     if (!strcmp(key, "split")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->split_override = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
@@ -445,6 +452,21 @@ int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const in
     if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
     const int rc = launch(plan, wave, offset, length, B, aug, noise, out_norm, out_db, out_melpow, normalize,
                           static_cast<cudaStream_t>(cuda_stream));
+    if (dev != plan->device) cudaSetDevice(dev);
+    return rc;
+}
+
+int lm_forward_pcm16(lm_plan* plan, const int16_t* pcm, const int64_t* offset, const int32_t* length, int32_t B,
+                     const lm_aug* aug, const float* noise, float* out_norm, int32_t normalize, void* cuda_stream) {
+    if (!plan || B < 0) return LM_ERR_INVALID_ARG;
+    if (B == 0) return LM_OK;
+    if (!pcm || !offset || !length || !out_norm) return LM_ERR_INVALID_ARG;
+    NvtxRange nvtx("lm_forward_pcm16");
+    int dev = -1;
+    LM_CUDA(cudaGetDevice(&dev));
+    if (dev != plan->device) LM_CUDA(cudaSetDevice(plan->device));
+    const int rc = launch(plan, reinterpret_cast<const float*>(pcm), offset, length, B, aug, noise, out_norm, nullptr, nullptr, normalize,
+                          static_cast<cudaStream_t>(cuda_stream), nullptr, 0, nullptr, true);
     if (dev != plan->device) cudaSetDevice(dev);
     return rc;
 }
@@ -723,7 +745,7 @@ static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, in
         const long long* d_off = reinterpret_cast<const long long*>(s.d_meta);
         const lm_aug* d_aug = reinterpret_cast<const lm_aug*>(s.d_meta + sizeof(long long) * cap);
         const int* d_len = reinterpret_cast<const int*>(s.d_meta + (sizeof(long long) + sizeof(lm_aug)) * cap);
-        if ((rc = grow(&s.d_wave, &s.cap_wave, std::max<size_t>(n_wave + 8, 16)))) break;
+        if (!pcm16 && (rc = grow(&s.d_wave, &s.cap_wave, std::max<size_t>(n_wave + 8, 16)))) break;
         if (pcm16 && (rc = grow(&s.d_pcm, &s.cap_pcm, std::max<size_t>(n_wave + 8, 16)))) break;
         if ((rc = grow(&s.d_out, &s.cap_out, clip_elems * n))) break;
         if (noise && (rc = grow(&s.d_noise, &s.cap_noise, static_cast<size_t>(plan->T) * n))) break;
@@ -734,19 +756,14 @@ static int forward_host_impl(lm_plan* plan, const void* wave_any, bool pcm16, in
         cudaError_t e = cudaMemcpyAsync(s.d_meta, s.h_meta, kMetaPerClip * cap, cudaMemcpyHostToDevice, s.stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy (metadata)"); break; }
         if (n_wave && !pcm16) e = cudaMemcpyAsync(s.d_wave, wave + lo, sizeof(float) * n_wave, cudaMemcpyHostToDevice, s.stream);
-        if (n_wave && pcm16) {
-            e = cudaMemcpyAsync(s.d_pcm, pcm + lo, sizeof(int16_t) * n_wave, cudaMemcpyHostToDevice, s.stream);
-            if (e == cudaSuccess) {
-                if ((rc = lm_pcm16_decode(s.d_pcm, s.d_wave, static_cast<int64_t>(n_wave), s.stream))) break;
-                plan->launches.fetch_add(1);
-            }
-        }
+        if (n_wave && pcm16) e = cudaMemcpyAsync(s.d_pcm, pcm + lo, sizeof(int16_t) * n_wave, cudaMemcpyHostToDevice, s.stream);
         if (e == cudaSuccess && noise)
             e = cudaMemcpyAsync(s.d_noise, noise + static_cast<size_t>(c0) * plan->T, sizeof(float) * plan->T * n,
                                 cudaMemcpyHostToDevice, s.stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
-        rc = launch(plan, s.d_wave, reinterpret_cast<const int64_t*>(d_off), d_len, n, aug ? d_aug : nullptr,
-                    noise ? s.d_noise : nullptr, s.d_out, nullptr, nullptr, normalize, s.stream);
+        rc = launch(plan, pcm16 ? reinterpret_cast<const float*>(s.d_pcm) : s.d_wave, reinterpret_cast<const int64_t*>(d_off), d_len, n,
+                    aug ? d_aug : nullptr, noise ? s.d_noise : nullptr, s.d_out, nullptr, nullptr, normalize, s.stream, nullptr, 0, nullptr,
+                    pcm16);
         if (rc) break;
         e = cudaMemcpyAsync(out + clip_elems * c0, s.d_out, sizeof(float) * clip_elems * n, cudaMemcpyDeviceToHost, s.stream);
         if (e != cudaSuccess) { rc = cuda_fail(e, "D2H copy"); break; }

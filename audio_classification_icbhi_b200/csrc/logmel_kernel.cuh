@@ -1,26 +1,18 @@
 // logmel_kernel.cuh -- the fused log-mel kernel for sm_100a (B200).
 //
-// One persistent CTA per SM, 16 warps in TWO ROLES (v7, warp-specialised):
-//
-//   warps 8-15  FFT warps.  They free-run: wait for a staged tile (mbarrier), pull their frame into registers,
-//               release the staging buffer, transform, wait for their power row to be free, write 4|X|^2 into it and
-//               signal the row.  No barrier among them, no integer work: two of them per scheduler keep the FMA pipe
-//               ~80 % busy (tools/ubench_fft_warps.cu: 464 cycles per frame per SM against 818 for the v6 kernel,
-//               whose warps all walked through FFT -> mel -> normalisation in lock step and left the FMA pipe idle
-//               43 % of the time).
-//   warps 0-7   everything else, concurrently: clip scheduling (the first gridDim clips are dealt statically, every
-//               further one is fetched with atomicAdd on a per-launch work counter, so ragged batches stay balanced),
-//               staging two tiles ahead of the mel phase (TMA bulk copy + gather), the mel GEMM on the tensor cores
-//               with its dB / mask / store epilogue, silent tiles, per-clip statistics and normalisation.
-//
-// The roles meet only through four pairs of mbarriers -- staged tile full / empty, power rows full / empty -- over
-// double-buffered staging buffers and power rows.  Each scheduler (warp % 4) runs two warps of either role: FMA-heavy
-// and tensor / load-store-heavy instruction streams side by side instead of one after the other.
+// One persistent CTA per SM, 16 warps = TWO INDEPENDENT GROUPS of 8 warps.  A group is a
+// "virtual CTA": it owns whole clips, one at a time (the first 2 * gridDim clips are dealt statically,
+// every further one is fetched with atomicAdd on a per-launch work counter, so ragged batches stay
+// balanced), walks the clip's (clip, tile) items on its own, and synchronises only with itself
+// (named barrier 1 + group, mbarrier [group]).  The groups share the constant tables in shared
+// memory and nothing else; two of them keep the scheduler's dispatch port busier than one 16-warp
+// CTA whose warps all sit in the same phase (the relative phase of the groups
+// does not matter, `stagger_ns` is kept as an experiment knob only).
 //
 // A tile is 8 frames (16 for n_fft = 1024); one warp = one frame.  Per item, inside a group:
 //
-//   stage   (two items ahead of the mel phase, into the buffer the FFT warps released) the tile's
-//           samples -> shared memory, once per sample although
+//   stage   (one item ahead, into the group's single buffer as soon as every warp has pulled its
+//           frame into registers) the tile's samples -> shared memory, once per sample although
 //           every sample feeds 4 frames.  The contiguous interior of a plain clip is one
 //           cp.async.bulk (TMA, 1-D) completing on an mbarrier; whatever is left -- torch.stft's
 //           reflect padding, zero padding, and whole tiles of augmented clips -- goes through the
@@ -42,16 +34,22 @@
 //           fp64 sum / sum-of-squares.
 //   silent  tiles that lie entirely in a plain clip's zero padding skip all of the above and write the floor /
 //           mask values and their statistics directly (bit-identical to the full path on a zero spectrum).
-//   split   small batches (B < number of CTAs on the GPU): a clip's tiles are dealt to `split` CTAs as
+//   split   small batches (B < number of groups on the GPU): a clip's tiles are dealt to `split` groups as
 //           "virtual clips" (clip, tile range); the per-clip statistics are 64-bit fixed-point sums (exact,
-//           order-independent integer adds), combined with atomics, and the CTA that arrives last
+//           order-independent integer adds), combined with atomics, and the group that arrives last
 //           normalises the whole clip.  Bit-identical to the unsplit path.
 //   norm    when the clip is finished the same group re-reads its (L2-resident) dB block and
 //           writes (x - mean) / (std + eps)  (R/src/data/preprocessing.py:111-116); for lm_forward_gather
 //           the same pass also stores the result into the other ranks' gathered buffers (multimem.st
 //           through the NVSwitch, or plain stores to peer-mapped memory).
 //
-// Algorithmic HBM bytes per clip: 4*min(len, T) read + 4*n_mels*frames written.
+//   pcm16   (PCM16 instantiation, lm_forward_pcm16) the clips are 16-bit PCM, the sample format of the ICBHI wav
+//           files (R/src/data/preprocessing.py:55-68 decodes them with torchaudio.load): the bulk copy brings the
+//           tile's raw samples (2 bytes each) to the END of the staging buffer and the group expands them in place to
+//           fp32 (x / 32768, as lm_pcm16_decode) before the FFT reads them; the gather path converts sample by sample.
+//           HBM sees 2 bytes per sample and there is no decode kernel in front.
+//
+// Algorithmic HBM bytes per clip: 4*min(len, T) read (2*min(len, T) for pcm16) + 4*n_mels*frames written.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,36 +57,43 @@
 #include "../../include/logmel_b200.h"
 #include "fft_gen.cuh"
 
+// Build-time experiment switches (tools/build_variants.py); the shipped kernel is LM_EXP=0, LM_TIMING=0.
+//   LM_EXP     1: no mel phase (FFT only)   2: no FFT (mel phase on stale rows)   3: no FFT part 2
+//   LM_TIMING  1: every warp accumulates clock64() deltas per phase into lm::g_timing[block][warp][8]
+//              (read back with lm_debug_timing)
+#ifndef LM_EXP
+#define LM_EXP 0
+#endif
+#ifndef LM_TIMING
+#define LM_TIMING 0
+#endif
 #ifndef LM_SILENT
 #define LM_SILENT 1   // 1: tiles that lie entirely in a plain clip's zero padding skip FFT and mel and write the floor
 #endif
-#ifndef LM_TIMING
-#define LM_TIMING 0   // 1 (tools/build_variants.py): every warp accumulates clock64() deltas per phase into lm::g_timing[block][warp][8]
+#ifndef LM_SKEW
+#define LM_SKEW 0   // 1: odd warps of a group apply the twiddle before barrier (A), even warps after it: the two
+                    //    halves then hit the shared-memory pipe (transposes) and the FMA pipe out of step
+#endif
+#ifndef LM_TW2
+#define LM_TW2 1   // 1: twiddle = product of two table entries (10 table rows); 0: full table (31 rows, 8 KB)
 #endif
 #if LM_TIMING
 #define LM_T(slot) do { const long long t_now_ = clock64(); t_acc[slot] += t_now_ - t_last; t_last = t_now_; } while (0)
 #else
 #define LM_T(slot) do { } while (0)
 #endif
-#ifndef LM_TW2
-#define LM_TW2 1   // 1: twiddle = product of two table entries (10 table rows); 0: full table (31 rows, 8 KB)
-#endif
 
 namespace lm {
 
 #if LM_TIMING
 __device__ long long g_timing[160 * 16 * 8];
-__device__ long long g_trace[64 * 8];   // CTA 0, first 64 ring items: 0 TMA issued, 1 FFT warp 8 sees the tile, 2 loaded, 3 rows free, 4 rows written, 5 mel warp 1 sees rows, 6 mel done, 7 iteration end
-#define LM_TR(item, ev) do { if (blockIdx.x == 0 && (item) < 64) g_trace[(item) * 8 + (ev)] = clock64(); } while (0)
 #endif
-constexpr int kGroups = 1;                    // scheduling units (clip owners) per CTA
-constexpr int kGroupWarps = 8;                // warps 0-7: staging, mel, epilogue, normalisation ("the group")
+
+constexpr int kGroups = 2;
+constexpr int kGroupWarps = 8;
 constexpr int kGroupThreads = kGroupWarps * 32;
-constexpr int kFftWarps = 8;                  // warps 8-15: one frame (n_fft 1024: two) of every tile each
-constexpr int kWarps = kGroupWarps + kFftWarps;
+constexpr int kWarps = kGroups * kGroupWarps;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCtxSlots = 8;                  // clip contexts in flight (scheduling runs three items ahead)
-constexpr int kCtxSlot = 80;                  // bytes per slot
 constexpr int kScrPitch = 36;                 // transpose rows: 32 + 4 (16 B aligned, LDS.128 conflict-free)
 constexpr int kRowFloats = 1168;              // per-warp row: >= 32*36 and == 16 (mod 32) for the MMA loads
 constexpr int kPbOff = 528;                   // n_fft=1024: second frame's spectrum inside the row (== 16 mod 32)
@@ -106,7 +111,7 @@ struct MelTable {                             // lives in global memory, copied 
 
 struct KParams {
     // batch
-    const float* __restrict__ wave;
+    const float* __restrict__ wave;       // PCM16 instantiation: const int16_t* in disguise (offsets count samples either way)
     const long long* __restrict__ offset;
     const int* __restrict__ length;
     const lm_aug* __restrict__ aug;
@@ -123,9 +128,9 @@ struct KParams {
     float* peer[kMaxPeers];
     int n_peer;
     float* mc_out;
-    // dynamic clip scheduling: clips [0, gridDim) are dealt statically (one per CTA); every further clip
-    // is fetched with atomicAdd on work_counter[0] when a CTA schedules the last tile of its current clip, so that
-    // ragged batches (unequal numbers of silent tiles) stay balanced.  work_counter[1] counts the CTAs that have
+    // dynamic clip scheduling: clips [0, 2*gridDim) are dealt statically (one per group); every further clip
+    // is fetched with atomicAdd on work_counter[0] when a group starts the last tile of its current clip, so that
+    // ragged batches (unequal numbers of silent tiles) stay balanced.  work_counter[1] counts the groups that have
     // finished; the last one puts both back to zero, so a launch needs no memset (the counters start at zero when
     // the plan is created and every launch leaves them at zero).
     int* work_counter;
@@ -141,6 +146,7 @@ struct KParams {
     int ns;          // staged floats per tile = (TILE_F-1)*hop + NFFT, rounded up to 4
     int n_dk;        // total 16-bin steps in melw
     int use_tma;
+    int stagger_ns;  // head start of group 0 over group 1
     float db_scale;  // db_multiplier * log10(2): dB = db_scale * log2(x) - db_offset
     float amin, db_offset, floor_db, norm_eps;
     const float* __restrict__ window;   // [NFFT] (the first half is used)
@@ -188,12 +194,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// barrier of warps 0-7 (id 1; id 0 is __syncthreads; the FFT warps use no named barrier)
-__device__ __forceinline__ void group_bar() {
-    asm volatile("bar.sync 1, %0;" ::"n"(kGroupThreads) : "memory");
+// barrier of one 8-warp group (ids 1 and 2; id 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
 }
 // D += A(16x8, row) * B(8x8, col), TF32 inputs (low 13 mantissa bits ignored), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -307,8 +310,9 @@ __device__ __forceinline__ void warp_twiddle(lm_f2 (&z)[32], const float2* __res
     }
 }
 __device__ __forceinline__ void warp_cfft1024_part2(lm_f2 (&z)[32], float (&xr)[32], float (&xi)[32],
-                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane) {
-    warp_twiddle(z, tw, lane);
+                                                    float* __restrict__ scr, const float2* __restrict__ tw, int lane,
+                                                    bool do_twiddle = true) {
+    if (do_twiddle) warp_twiddle(z, tw, lane);
     lm_f2 pr[16], pi[16];
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) scr[k1 * kScrPitch + lane] = lm_lo(z[k1]);
@@ -368,16 +372,8 @@ __device__ __noinline__ void stage_noisy_tile(const ClipCtx& c, float* __restric
 template <int NFFT>
 struct Geo {
     static constexpr int FPW = (NFFT == 2048) ? 1 : 2;   // frames per warp pass
-    static constexpr int TILE_F = kFftWarps * FPW;       // frames per item
+    static constexpr int TILE_F = kGroupWarps * FPW;     // frames per item
     static constexpr int NB = TILE_F / 8;                // 8-frame MMA column blocks per tile
-};
-
-// One entry of the item ring the scheduling thread fills three items ahead of the mel phase.
-struct alignas(16) ItemDesc {
-    int slot;     // clip context slot
-    int tile;     // tile of the clip
-    int flags;    // bit 0: valid (0 = the CTA's work is exhausted), bit 1: silent tile, bit 2: last tile of its (virtual) clip
-    int pad;
 };
 
 // Shared-memory carve-up, shared by host (size) and device (pointers).  Everything of fixed size
@@ -385,29 +381,29 @@ struct alignas(16) ItemDesc {
 // the run-time sized arrays (staging buffers, filterbank) sit at the end.
 template <int NFFT>
 struct Smem {
-    static constexpr size_t kBar = 0;                                    // 8 mbarriers: staged tile full[2] / empty[2], power rows full[2] / empty[2];
-                                                                         // +64 the filterbank-copy mbarrier, +72 'go' flags of the two staging buffers
-    static constexpr size_t kRed = kBar + 96;                            // reduction scratch + bcast[3]: mean, std + eps, 'this CTA normalises'
-    static constexpr size_t kDesc = kRed + sizeof(long long) * 2 * kGroupWarps + 16;   // 4 item descriptors
-    static constexpr size_t kCtx = kDesc + 4 * sizeof(ItemDesc);         // clip contexts
-    static constexpr size_t kTab = kCtx + kCtxSlots * kCtxSlot;
+    static constexpr size_t kBar = 0;                                    // kGroups mbarriers + 'TMA pending' flags
+    static constexpr size_t kRed = kBar + 48;                            // + the filterbank-copy mbarrier at +32                            // per group: reduction scratch + broadcast
+    static constexpr size_t kRedGroup = sizeof(long long) * 2 * kGroupWarps + 16;   // + bcast[3]: mean, std + eps, 'this group normalises'
+    static constexpr size_t kCtx = kRed + kGroups * kRedGroup;           // per group two ClipCtx slots (ordinal & 1)
+    static constexpr size_t kTab = kCtx + kGroups * 2 * 80;
     static constexpr size_t kStat = kTab + ((sizeof(MelTable) + 15) & ~size_t(15));   // per-thread fixed-point (sum, sumsq)
-    static constexpr size_t kWin = kStat + sizeof(double) * 2 * kGroupThreads;
+    static constexpr size_t kWin = kStat + sizeof(double) * 2 * kThreads;
     static constexpr size_t kTw = kWin + sizeof(float) * (NFFT / 2);     // first half of the window
     static constexpr size_t kUtw = kTw + sizeof(float2) * 32 * kTwRows;
     static constexpr size_t kScr = kUtw + ((NFFT == 2048) ? sizeof(float2) * 512 : 0);
-    static constexpr size_t kSbuf = kScr + sizeof(float) * 2 * kFftWarps * kRowFloats;   // two sets of power rows
-    static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0 && kDesc % 16 == 0, "alignment");
-    static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * 2 * static_cast<size_t>(ns); }   // two staging buffers
+    static constexpr size_t kSbuf = kScr + sizeof(float) * kWarps * kRowFloats;
+    static_assert(kSbuf % 16 == 0 && kScr % 16 == 0 && kStat % 16 == 0 && kCtx % 16 == 0 && kRedGroup % 16 == 0, "alignment");
+    static __host__ __device__ size_t melw_offset(int ns) { return kSbuf + sizeof(float) * kGroups * static_cast<size_t>(ns); }
     static __host__ __device__ size_t total(int ns, int n_dk) {
         return melw_offset(ns) + sizeof(float4) * 64 * static_cast<size_t>(n_dk);
     }
 };
 
-// Everything the staging and epilogue code needs to know about one clip.  kCtxSlots of them live in shared memory
-// (the scheduling thread runs three items ahead of the epilogue and a virtual clip can be a single tile).
+// Everything the staging and epilogue code needs to know about one clip.  Two slots per group live
+// in shared memory (clip ordinal & 1: staging runs one item ahead of the epilogue) so that none of
+// it occupies registers across the FFT.
 struct alignas(16) ClipCtx {
-    const float* src;    // first sample after the centre crop
+    const float* src;    // first sample after the centre crop (PCM16: a const short* in disguise)
     const float* nz;     // host-drawn noise row or nullptr
     uint64_t seed;
     int lc;              // valid samples after pad/crop
@@ -448,9 +444,10 @@ __device__ __noinline__ void stage_noisy_tile(const ClipCtx& c, float* __restric
         *reinterpret_cast<float4*>(sb + 4 * q) = make_float4(v4[0], v4[1], v4[2], v4[3]);
     }
 }
+constexpr int kCtxSlot = 80;
 static_assert(sizeof(ClipCtx) <= kCtxSlot && kCtxSlot % 16 == 0, "ClipCtx slot size");
 
-__device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* __restrict__ c, int nfft) {
+__device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* __restrict__ c, int nfft, bool pcm16 = false) {
     const int clip = vclip / p.split, chunk = vclip - clip * p.split;
     c->t_begin = chunk * p.tiles_per_chunk;
     c->t_end = (c->t_begin + p.tiles_per_chunk < p.n_tiles) ? c->t_begin + p.tiles_per_chunk : p.n_tiles;
@@ -459,7 +456,7 @@ __device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* 
     const int crop = len > p.T ? (len - p.T) / 2 : 0;       // centre crop
     c->clip = clip;
     c->lc = len < p.T ? len : p.T;
-    c->src = p.wave + off + crop;
+    c->src = pcm16 ? reinterpret_cast<const float*>(reinterpret_cast<const short*>(p.wave) + off + crop) : p.wave + off + crop;
     int shift = 0, f0 = 0, f1 = 0, t0 = 0, t1 = 0;
     float nscale = 0.0f, gain = 1.0f;
     uint64_t seed = 0;
@@ -492,11 +489,12 @@ __device__ __forceinline__ void load_clip(const KParams& p, int vclip, ClipCtx* 
     c->silent_from = silent_from;
 }
 
-// FASTNOISE: tiles of clips with on-device Philox noise are staged four samples per thread (stage_noisy_tile).  The
-// host launches this instantiation only when the batch can contain such clips (augmentation records given, no
-// host-drawn noise tensor); the headline path keeps FASTNOISE = false.
-template <int NFFT, bool EXTRA_OUT, bool FASTNOISE = false>
+// FASTNOISE: tiles of clips with on-device Philox noise are staged four samples per thread (stage_noisy_tile).  The call
+// costs the main loop ~3 % (registers live across it), so the host launches this instantiation only when the batch can
+// contain such clips (augmentation records given, no host-drawn noise tensor); the headline path keeps FASTNOISE = false.
+template <int NFFT, bool EXTRA_OUT, bool FASTNOISE = false, bool PCM16 = false>
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
+    static_assert(!(PCM16 && (FASTNOISE || EXTRA_OUT)), "the 16-bit instantiation is the plain one");
     using G = Geo<NFFT>;
     constexpr int TILE_F = G::TILE_F;
     constexpr int HALF = NFFT / 2;
@@ -504,123 +502,307 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using L = Smem<NFFT>;
     const int tid = threadIdx.x, lane_ = tid & 31;
+    const int group = tid >> 8;                       // warp-uniform
+    const int gtid = tid & (kGroupThreads - 1), gwarp_ = gtid >> 5;
 
-    uint64_t* const sb_full = reinterpret_cast<uint64_t*>(smem_raw + L::kBar);          // [2] a tile's samples are staged
-    uint64_t* const sb_empty = sb_full + 2;                                              // [2] every FFT warp has pulled its frame
-    uint64_t* const rows_full = sb_full + 4;                                             // [2] the tile's power rows are written
-    uint64_t* const rows_empty = sb_full + 6;                                            // [2] every mel warp is done with them
-    uint64_t* const mbar_fb = sb_full + 8;                                               // the filterbank copy
-    volatile int* const s_go = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 72); // [2] 1: transform the staged tile, 0: no more work
-    long long* const red = reinterpret_cast<long long*>(smem_raw + L::kRed);
-    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + sizeof(long long) * 2 * kGroupWarps);
-    ItemDesc* const s_desc = reinterpret_cast<ItemDesc*>(smem_raw + L::kDesc);
-    ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + L::kBar) + group;
+    volatile int* const s_pend = reinterpret_cast<volatile int*>(smem_raw + L::kBar + 16) + group;
+    long long* const red = reinterpret_cast<long long*>(smem_raw + L::kRed + group * L::kRedGroup);
+    float* const bcast = reinterpret_cast<float*>(smem_raw + L::kRed + group * L::kRedGroup + sizeof(long long) * 2 * kGroupWarps);
+    ClipCtx* const s_ctx = reinterpret_cast<ClipCtx*>(smem_raw + L::kCtx) + 2 * group;
     const MelTable* const s_tab = reinterpret_cast<const MelTable*>(smem_raw + L::kTab);
     longlong2* const s_stat = reinterpret_cast<longlong2*>(smem_raw + L::kStat);
     float* const s_win = reinterpret_cast<float*>(smem_raw + L::kWin);
     float2* const s_tw = reinterpret_cast<float2*>(smem_raw + L::kTw);
     float2* const s_utw = reinterpret_cast<float2*>(smem_raw + L::kUtw);
-    float* const rows = reinterpret_cast<float*>(smem_raw + L::kScr);                    // [2][kFftWarps][kRowFloats]
-    float* const sb = reinterpret_cast<float*>(smem_raw + L::kSbuf);                     // [2][ns]
+    float* const rows = reinterpret_cast<float*>(smem_raw + L::kScr) + group * (kGroupWarps * kRowFloats);
+    float* const sb = reinterpret_cast<float*>(smem_raw + L::kSbuf) + static_cast<size_t>(group) * p.ns;
     float4* const s_melw = reinterpret_cast<float4*>(smem_raw + L::melw_offset(p.ns));
-    constexpr int kRowSet = kFftWarps * kRowFloats;
 
     // ---- constants -> shared memory, once per (persistent) CTA, by all 16 warps -----------------
     for (int i = tid; i < HALF; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 32 * kTwRows; i += kThreads) s_tw[i] = p.tw[i];
     if (NFFT == 2048)
         for (int i = tid; i < 512; i += kThreads) s_utw[i] = p.utw[i];
+    // the banded filterbank (up to 96 KB) is needed first in the mel phase of the first item: one bulk copy, in flight
+    // during the first FFT, completing on its own mbarrier (every thread waits for it once, before its first mel phase)
+    uint64_t* const mbar_fb = reinterpret_cast<uint64_t*>(smem_raw + L::kBar + 32);
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&sb_full[b], 1);             // the staging thread (its arrival carries the bulk copy's byte count)
-            mbar_init(&sb_empty[b], kFftWarps);    // one arrival per FFT warp
-            mbar_init(&rows_full[b], kFftWarps);
-            mbar_init(&rows_empty[b], kGroupWarps);
-        }
         mbar_init(mbar_fb, 1);
         fence_mbar_init();
-        // the banded filterbank (up to 96 KB) is needed first in the mel phase of the first item: one bulk copy, in flight
-        // during the first FFT, completing on its own mbarrier (every mel thread waits for it once)
         mbar_expect_tx(mbar_fb, static_cast<uint32_t>(p.n_dk) * 1024u);
         bulk_g2s(s_melw, p.melw, static_cast<uint32_t>(p.n_dk) * 1024u, mbar_fb);
     }
     for (int i = tid; i < static_cast<int>(sizeof(MelTable) / 4); i += kThreads)
         reinterpret_cast<int*>(smem_raw + L::kTab)[i] = reinterpret_cast<const int*>(p.mel_table)[i];
-    for (int i = tid; i < 2 * kRowSet; i += kThreads) rows[i] = 0.0f;   // pad columns stay finite
-    for (int i = tid; i < 2 * p.ns; i += kThreads) sb[i] = 0.0f;
-    __syncthreads();   // the only CTA-wide barrier: from here on the two roles meet through mbarriers only
+    for (int i = gtid; i < kGroupWarps * kRowFloats; i += kGroupThreads) rows[i] = 0.0f;   // pad columns stay finite
+    for (int i = gtid; i < p.ns; i += kGroupThreads) sb[i] = 0.0f;
+    if (gtid == 0) {
+        mbar_init(mbar, 1);
+        fence_mbar_init();
+        *s_pend = 0;
+    }
+    __syncthreads();   // the only CTA-wide barrier: from here on the groups never meet again
 
-    const int hop = p.hop;
+    // ---- this group's clips -----------------------------------------------------------------------
+    const int nv = static_cast<int>(gridDim.x) * kGroups;
+    const int n_virtual = p.B * p.split;
+    const int clip0 = group * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);   // first (virtual) clip: static
+    if (clip0 >= n_virtual) return;
 
-#ifndef LM_FFT_FIRST
-#define LM_FFT_FIRST 0   // 1: warps 0-7 are the FFT warps (experiment: which role the scheduler serves first)
-#endif
-    const bool is_fft = LM_FFT_FIRST ? (tid < kFftWarps * 32) : (tid >= kGroupThreads);
-    const int rtid = LM_FFT_FIRST ? (is_fft ? tid : tid - kFftWarps * 32) : (is_fft ? tid - kGroupThreads : tid);   // thread index inside the role
-    if (is_fft) {
-        // =================================================================================================
-        // FFT warps: staged tile -> 4|X|^2 rows.  Ring item r uses staging buffer and row set r & 1.
-        // =================================================================================================
-        const int lane = lane_, fw = rtid >> 5;
+    const int T = p.T, hop = p.hop, frames = p.frames, n_mels = p.n_mels;
+    const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
+
+    uint32_t parity = 0;                   // mbarrier phase of the staging buffer (group-uniform)
+
+    // ---- staging of one item into the group's buffer -------------------------------------------------
+    // bulk part: [e_lo, e_lo + cnt) of the tile is src[j0 + e_lo ...] verbatim (plain clips only)
+    auto bulk_range = [&](const ClipCtx* __restrict__ c, int tile_, int& e_lo, int& cnt) {
+        e_lo = 0; cnt = 0;
+        if (!p.use_tma || !c->plain) return;
+        const int tf = tile_ * TILE_F;
+        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+        const int need = (nf - 1) * hop + NFFT;
+        const int j0 = tf * hop - HALF;
+        const int lo = j0 < 0 ? -j0 : 0;
+        int hi = c->lc - j0;
+        if (hi > need) hi = need;
+        if (hi <= lo) return;
+        if (PCM16) {   // 16 bytes = 8 samples
+            if ((reinterpret_cast<uintptr_t>(reinterpret_cast<const short*>(c->src) + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
+            e_lo = lo;
+            cnt = (hi - lo) & ~7;
+            return;
+        }
+        if ((reinterpret_cast<uintptr_t>(c->src + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
+        e_lo = lo;
+        cnt = (hi - lo) & ~3;
+    };
+    auto tile_silent = [&](const ClipCtx* __restrict__ c, int tile_) -> bool {   // group-uniform
+        return LM_SILENT && tile_ >= c->silent_from;
+    };
+    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_) {   // ONE thread of the group
+        int e_lo, cnt;
+        bulk_range(c, tile_, e_lo, cnt);
+        if (cnt != 0) {
+            const int j0 = tile_ * TILE_F * hop - HALF;
+            fence_proxy_async();
+            if (PCM16) {   // raw samples to the end of the buffer; stage_gather expands them in place
+                mbar_expect_tx(mbar, static_cast<uint32_t>(cnt) * 2u);
+                bulk_g2s(reinterpret_cast<unsigned char*>(sb) + 4 * p.ns - 2 * cnt, reinterpret_cast<const short*>(c->src) + j0 + e_lo,
+                         static_cast<uint32_t>(cnt) * 2u, mbar);
+            } else {
+                mbar_expect_tx(mbar, static_cast<uint32_t>(cnt) * 4u);
+                bulk_g2s(sb + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u, mbar);
+            }
+        }
+        *s_pend = (cnt != 0 ? 1 : 0) | (tile_silent(c, tile_) ? 2 : 0);   // bit 0: bulk copy pending, bit 1: silent tile
+    };
+    // returns (group-uniform) whether anything was written
+    auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_) -> bool {   // all threads of the group
+        if (tile_silent(cc, tile_)) return false;   // nobody will read the buffer
+        int e_lo, cnt;
+        bulk_range(cc, tile_, e_lo, cnt);
+        if (PCM16 && cnt != 0) {
+            // The bulk copy left the raw samples of [e_lo, e_lo + cnt) in the last 2 cnt bytes of the buffer.  Expand them
+            // to fp32 in place, 8 samples (16 bytes) per step and thread: every thread of a batch reads before any writes
+            // (barrier), and a chunk's fp32 image never reaches the raw bytes of a LATER chunk (4 e_lo + 32 (c + 1) <=
+            // 4 ns - 2 cnt + 16 c' for c' > c), so the batches can follow each other without a second barrier.
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            const int nch = cnt >> 3;
+            const uint4* __restrict__ rawp = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(sb) + 4 * p.ns - 2 * cnt);
+            float4* __restrict__ dst = reinterpret_cast<float4*>(sb + e_lo);
+            constexpr float k = 1.0f / 32768.0f;   // as lm_pcm16_decode
+            for (int c0 = 0; c0 < nch; c0 += 3 * kGroupThreads) {
+                uint4 raw[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int ch = c0 + u * kGroupThreads + gtid;
+                    if (ch < nch) raw[u] = rawp[ch];
+                }
+                group_bar(group);
+                if (c0 == 0 && gtid == 0) *s_pend = *s_pend & ~1;   // the copy has been waited for here, not at the top of the item
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int ch = c0 + u * kGroupThreads + gtid;
+                    if (ch < nch) {
+                        const int4 v = make_int4(static_cast<int>(raw[u].x), static_cast<int>(raw[u].y), static_cast<int>(raw[u].z), static_cast<int>(raw[u].w));
+                        dst[2 * ch] = make_float4(static_cast<float>(static_cast<short>(v.x & 0xffff)) * k, static_cast<float>(v.x >> 16) * k,
+                                                  static_cast<float>(static_cast<short>(v.y & 0xffff)) * k, static_cast<float>(v.y >> 16) * k);
+                        dst[2 * ch + 1] = make_float4(static_cast<float>(static_cast<short>(v.z & 0xffff)) * k, static_cast<float>(v.z >> 16) * k,
+                                                      static_cast<float>(static_cast<short>(v.w & 0xffff)) * k, static_cast<float>(v.w >> 16) * k);
+                    }
+                }
+            }
+        }
+        const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
+        if (rest <= 0) return PCM16 && cnt != 0;
+        const ClipCtx c = *cc;
+        const int tf = tile_ * TILE_F;
+        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+        const int need = (nf - 1) * hop + NFFT;
+        const int j0 = tf * hop - HALF;
+        // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
+        // feed only frames >= `frames` and are zeroed
+        if (FASTNOISE && c.nscale != 0.0f && c.nz == nullptr && cnt == 0) {   // on-device noise (training batches): out of line
+            stage_noisy_tile(*cc, sb, p.ns, need, j0, T, gtid);   // the context in shared memory, not the register copy
+            return true;
+        }
+        for (int idx = gtid; idx < rest; idx += kGroupThreads) {
+            const int e = idx < e_lo ? idx : idx + cnt;
+            int j = j0 + e;
+            if (j < 0) j = -j;
+            else if (j >= T) j = 2 * (T - 1) - j;
+            float v = 0.0f;
+            if (e < need && j >= 0 && j < T) {
+                int i = j - c.shift;               // torch.roll: out[j] = in[(j - shift) mod T]
+                if (i < 0) i += T;
+                else if (i >= T) i -= T;
+                if (i < c.lc)
+                    v = (PCM16 ? static_cast<float>(__ldg(reinterpret_cast<const short*>(c.src) + i)) * (1.0f / 32768.0f) : __ldg(c.src + i)) * c.gain;
+                if (c.nscale != 0.0f) {
+                    const float z = c.nz ? __ldg(c.nz + i) : philox_normal(c.seed, static_cast<uint32_t>(i));
+                    v = fmaf(z, c.nscale, v);
+                }
+            }
+            sb[e] = v;
+        }
+        return true;
+    };
+
+    // ---- prologue: item 0 is staged before the loop; item it+1 is staged during item it ----------------
+    if (gtid == 0) {
+        load_clip(p, clip0, &s_ctx[0], NFFT, PCM16);
+        stage_bulk(&s_ctx[0], s_ctx[0].t_begin);
+    }
+    group_bar(group);
+    stage_gather(&s_ctx[0], s_ctx[0].t_begin);
+    group_bar(group);
+    if (group == 1 && p.stagger_ns > 0) {   // spin (nanosleep may return early): ~2 cycles per ns
+        const long long t_end = clock64() + 2LL * p.stagger_ns;
+        while (clock64() < t_end) {}
+    }
+
+    bool fb_ready = false;                 // this thread has seen the filterbank copy complete
+    s_stat[tid] = make_longlong2(0, 0);    // this thread's running (sum, sum of squares) of the clip's dB values, fixed point
+    int tile = s_ctx[0].t_begin, t_end = s_ctx[0].t_end, ord = 0, clip = s_ctx[0].clip;   // tile, end of the tile range, clip ordinal (context slot = ord & 1), clip index
+
 #if LM_TIMING
-        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        long long t_last = clock64();
+    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = clock64();
 #endif
 #pragma unroll 1
-        for (uint32_t r = 0;; ++r) {
-            const uint32_t b = r & 1u, ph = (r >> 1) & 1u;
-            mbar_wait(&sb_full[b], ph);
-            LM_T(0);
-#if LM_TIMING
-            if (rtid == 0) LM_TR(r, 1);
-#endif
-            if (s_go[b] == 0) break;
-            const float* __restrict__ sbuf = sb + b * p.ns;
-            float* const scr = rows + b * kRowSet + fw * kRowFloats;
-            // ---- window + first butterfly stage (hann[n + NFFT/2] = 1 - hann[n]) + rest of FFT part 1 (registers) ----
-            // a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
-            lm_f2 z[32];
+    for (;;) {
+        const int tf = tile * TILE_F;                  // first frame of the tile
+        const int st_item = *s_pend;
+        if (st_item & 1) {
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+        }
+        LM_T(0);   // staging wait
+
+        // ---- window + first butterfly stage + rest of FFT part 1 (registers; reads the staged samples) ----
+        // hann[n + NFFT/2] = 1 - hann[n]:  a = v1 w + v2 (1 - w) = (v1 - v2) w + v2,  b = v1 w - v2 (1 - w) = (v1 + v2) w - v2
+        // item it+1: its TMA part goes into the buffer consumed by (A); one thread; the clip's context slot is
+        // filled when its first tile comes up
+        const bool wrap = (tile + 1 == t_end);   // last tile of this (virtual) clip
+        int tile1 = tile + 1, ord1 = ord;        // tile1 of a new clip is its t_begin: read from the context after barrier (B)
+        if (wrap) ++ord1;
+        auto issue_next = [&]() {
+            if (gtid == 0) {
+                ClipCtx* const cn = &s_ctx[ord1 & 1];
+                if (wrap) {   // fetch the group's next (virtual) clip
+                    const int nxt = nv + atomicAdd(p.work_counter, 1);
+                    if (nxt < n_virtual) {
+                        load_clip(p, nxt, cn, NFFT, PCM16);
+                        stage_bulk(cn, cn->t_begin);
+                    } else {
+                        cn->clip = -1;
+                    }
+                } else {
+                    stage_bulk(cn, tile1);
+                }
+            }
+        };
+        if (__builtin_expect((st_item & 2) != 0, 0)) {
+            group_bar(group);   // (A)
+            issue_next();
+            group_bar(group);   // (B)
+            // ---- silent tile: every feature is the floor (or a mask's 0) ----------------------------------------
+            const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+            const ClipCtx* __restrict__ cx = &s_ctx[ord & 1];
+            float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+            float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+            const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
+            float ssum = 0.0f, qsum = 0.0f;
+            for (int idx = gtid; idx < n_mels * TILE_F; idx += kGroupThreads) {
+                const int m = idx / TILE_F, f = idx - m * TILE_F, tt = tf + f;
+                if (f < nf) {
+                    const float v = ((m >= cf0 && m < cf1) || (tt >= ct0 && tt < ct1)) ? 0.0f : p.floor_db;
+                    const int o = m * frames + tt;
+                    out[o] = v;
+                    if (EXTRA_OUT) {
+                        if (odb) odb[o] = v;
+                        if (omp) omp[o] = 0.0f;
+                    }
+                    ssum += v;
+                    qsum = fmaf(v, v, qsum);
+                }
+            }
+            stat_add(&s_stat[tid], ssum, qsum);
+        } else {
+        lm_f2 z[32];
+        if (LM_EXP != 2) {
+            const int lane = launder(lane_), gw = launder(gwarp_);
             if (NFFT == 2048) {
-                const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sbuf + fw * hop);
+                const float2* __restrict__ s2 = reinterpret_cast<const float2*>(sb + gw * hop);
                 const float2* __restrict__ w2 = reinterpret_cast<const float2*>(s_win);
 #pragma unroll
-                for (int r_ = 0; r_ < 16; ++r_) {
-                    const float2 v1 = s2[32 * r_ + lane];
-                    const float2 v2 = s2[32 * (r_ + 16) + lane];
-                    const float2 w = w2[32 * r_ + lane];
+                for (int r = 0; r < 16; ++r) {
+                    const float2 v1 = s2[32 * r + lane];
+                    const float2 v2 = s2[32 * (r + 16) + lane];
+                    const float2 w = w2[32 * r + lane];
                     const lm_f2 V1 = lm_pack(v1.x, v1.y), V2 = lm_pack(v2.x, v2.y), W = lm_pack(w.x, w.y);
-                    z[r_] = lm_fma2(lm_sub2(V1, V2), W, V2);
-                    z[r_ + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-v2.x, -v2.y));
+                    z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
+                    z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-v2.x, -v2.y));
                 }
             } else {
                 // n_fft = 1024: two frames per warp as one complex signal z = a + i b
-                const float* __restrict__ sa = sbuf + (2 * fw) * hop;
+                const float* __restrict__ sa = sb + (2 * gw) * hop;
                 const float* __restrict__ sbb = sa + hop;
 #pragma unroll
-                for (int r_ = 0; r_ < 16; ++r_) {
-                    const float a1 = sa[32 * r_ + lane], a2 = sa[32 * (r_ + 16) + lane];
-                    const float b1 = sbb[32 * r_ + lane], b2 = sbb[32 * (r_ + 16) + lane];
-                    const lm_f2 V1 = lm_pack(a1, b1), V2 = lm_pack(a2, b2), W = lm_bcast(s_win[32 * r_ + lane]);
-                    z[r_] = lm_fma2(lm_sub2(V1, V2), W, V2);
-                    z[r_ + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-a2, -b2));
+                for (int r = 0; r < 16; ++r) {
+                    const float a1 = sa[32 * r + lane], a2 = sa[32 * (r + 16) + lane];
+                    const float b1 = sbb[32 * r + lane], b2 = sbb[32 * (r + 16) + lane];
+                    const lm_f2 V1 = lm_pack(a1, b1), V2 = lm_pack(a2, b2), W = lm_bcast(s_win[32 * r + lane]);
+                    z[r] = lm_fma2(lm_sub2(V1, V2), W, V2);
+                    z[r + 16] = lm_fma2(lm_add2(V1, V2), W, lm_pack(-a2, -b2));
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sb_empty[b]);   // the frame is in registers: the buffer may be restaged
-#if LM_TIMING
-            if (rtid == 0) LM_TR(r, 2);
-#endif
             lm_fft32_aos_from2(z);
-            LM_T(1);
-            mbar_wait(&rows_empty[b], ph ^ 1u);         // the mel warps are done with this row's previous tile
-            LM_T(2);
-#if LM_TIMING
-            if (rtid == 0) LM_TR(r, 3);
-#endif
+            if (LM_SKEW && (gw & 1)) warp_twiddle(z, s_tw, lane);
+        }
+        LM_T(1);   // FFT part 1
+        group_bar(group);   // (A) every warp of the group is done with the mel phase of the previous item
+                            //     (rows are free) and with this item's staged samples (buffer is free)
 
-            // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
+        LM_T(2);   // barrier A
+        issue_next();
+
+        // ---- FFT part 2: transpose, second FFT, untangle -> 4|X|^2 in the warp's row ----------------------------
+        if (LM_EXP == 3) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += lm_lo(z[k]) + lm_hi(z[k]);
+            rows[gwarp_ * kRowFloats + lane_] = acc;
+        }
+        if (LM_EXP != 2 && LM_EXP != 3) {
+            const int lane = launder(lane_), gw = launder(gwarp_);
+            float* const scr = rows + gw * kRowFloats;
             float xr[32], xi[32];
-            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane);
+            warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane, !(LM_SKEW && (gw & 1)));
             const int srcl = (32 - lane) & 31;
             const bool l0 = (lane == 0);
             if (NFFT == 2048) {
@@ -685,250 +867,48 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     Pb[512] = 4.0f * z16i * z16i;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rows_full[b]);
-            LM_T(3);
-#if LM_TIMING
-            if (rtid == 0) LM_TR(r, 4);
-#endif
         }
-#if LM_TIMING
-        if (lane_ == 0) {
-            long long* o = g_timing + (static_cast<size_t>(blockIdx.x) * kWarps + (tid >> 5)) * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = t_acc[i];
-        }
-#endif
-        return;
-    }
+        LM_T(3);   // FFT part 2 (+ TMA issue)
+        group_bar(group);   // (B) all power rows of the tile are in shared memory
+        LM_T(4);   // barrier B
 
-    // =====================================================================================================
-    // Warps 0-7: scheduling, staging, mel, epilogue, normalisation
-    // =====================================================================================================
-    const int gtid = rtid, gwarp_ = rtid >> 5;
-    const int nv = static_cast<int>(gridDim.x);
-    const int n_virtual = p.B * p.split;
-    const int T = p.T, frames = p.frames, n_mels = p.n_mels;
-    const size_t clip_elems = static_cast<size_t>(n_mels) * frames;
-
-    // ---- staging of one tile into a staging buffer ---------------------------------------------------------
-    // bulk part: [e_lo, e_lo + cnt) of the tile is src[j0 + e_lo ...] verbatim (plain clips only)
-    auto bulk_range = [&](const ClipCtx* __restrict__ c, int tile_, int& e_lo, int& cnt) {
-        e_lo = 0; cnt = 0;
-        if (!p.use_tma || !c->plain) return;
-        const int tf = tile_ * TILE_F;
-        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-        const int need = (nf - 1) * hop + NFFT;
-        const int j0 = tf * hop - HALF;
-        const int lo = j0 < 0 ? -j0 : 0;
-        int hi = c->lc - j0;
-        if (hi > need) hi = need;
-        if (hi <= lo) return;
-        if ((reinterpret_cast<uintptr_t>(c->src + j0 + lo) & 15u) != 0 || (lo & 3) != 0) return;
-        e_lo = lo;
-        cnt = (hi - lo) & ~3;
-    };
-    // ONE thread: the bulk copy (if any) and the arrival that hands the buffer to the FFT warps
-    auto stage_bulk = [&](const ClipCtx* __restrict__ c, int tile_, float* __restrict__ sbuf, uint64_t* bar) {
-        int e_lo, cnt;
-        bulk_range(c, tile_, e_lo, cnt);
-        if (cnt != 0) {
-            const int j0 = tile_ * TILE_F * hop - HALF;
-            fence_proxy_async();
-            mbar_expect_tx(bar, static_cast<uint32_t>(cnt) * 4u);
-            bulk_g2s(sbuf + e_lo, c->src + j0 + e_lo, static_cast<uint32_t>(cnt) * 4u, bar);
-        } else {
-            mbar_arrive(bar);
-        }
-    };
-    // all threads of the group; returns (group-uniform) whether anything was written
-    auto stage_gather = [&](const ClipCtx* __restrict__ cc, int tile_, float* __restrict__ sbuf) -> bool {
-        int e_lo, cnt;
-        bulk_range(cc, tile_, e_lo, cnt);
-        const int rest = p.ns - cnt;   // slots the bulk copy does not cover: [0, e_lo) and [e_lo + cnt, ns)
-        if (rest <= 0) return false;
-        const ClipCtx c = *cc;
-        const int tf = tile_ * TILE_F;
-        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-        const int need = (nf - 1) * hop + NFFT;
-        const int j0 = tf * hop - HALF;
-        // reflect (torch.stft center=True) -> roll -> pad/crop -> gain, + noise; slots past `need`
-        // feed only frames >= `frames` and are zeroed
-        if (FASTNOISE && c.nscale != 0.0f && c.nz == nullptr && cnt == 0) {   // on-device noise (training batches): out of line
-            stage_noisy_tile(*cc, sbuf, p.ns, need, j0, T, gtid);   // the context in shared memory, not the register copy
-            return true;
-        }
-        for (int idx = gtid; idx < rest; idx += kGroupThreads) {
-            const int e = idx < e_lo ? idx : idx + cnt;
-            int j = j0 + e;
-            if (j < 0) j = -j;
-            else if (j >= T) j = 2 * (T - 1) - j;
-            float v = 0.0f;
-            if (e < need && j >= 0 && j < T) {
-                int i = j - c.shift;               // torch.roll: out[j] = in[(j - shift) mod T]
-                if (i < 0) i += T;
-                else if (i >= T) i -= T;
-                if (i < c.lc) v = __ldg(c.src + i) * c.gain;
-                if (c.nscale != 0.0f) {
-                    const float z = c.nz ? __ldg(c.nz + i) : philox_normal(c.seed, static_cast<uint32_t>(i));
-                    v = fmaf(z, c.nscale, v);
-                }
-            }
-            sbuf[e] = v;
-        }
-        return true;
-    };
-
-    // ---- scheduling (thread 0): the CTA's stream of items, three ahead of the mel phase ---------------------
-    int sc_slot = 0, sc_tile = 0, sc_end = 0;
-    bool sc_done = false;
-    auto sched = [&](int j) {   // thread 0 only: fill s_desc[j & 3]
-        ItemDesc* const d = &s_desc[j & 3];
-        if (sc_done) { d->flags = 0; return; }
-        const ClipCtx* const c = &s_ctx[sc_slot];
-        int flags = 1 | ((LM_SILENT && sc_tile >= c->silent_from) ? 2 : 0);
-        d->slot = sc_slot; d->tile = sc_tile;
-        if (++sc_tile == sc_end) {   // the (virtual) clip ends with this tile: fetch the CTA's next one
-            flags |= 4;
-            const int nxt = nv + atomicAdd(p.work_counter, 1);
-            if (nxt < n_virtual) {
-                sc_slot = (sc_slot + 1) & (kCtxSlots - 1);
-                load_clip(p, nxt, &s_ctx[sc_slot], NFFT);
-                sc_tile = s_ctx[sc_slot].t_begin; sc_end = s_ctx[sc_slot].t_end;
-            } else {
-                sc_done = true;
-            }
-        }
-        d->flags = flags;
-    };
-    // ---- staging of item j (all threads of the group): ring bookkeeping is thread-uniform -------------------
-    uint32_t rs = 0;           // ring items staged so far
-    bool stop_sent = false;
-    auto stage_item = [&](int j) {
-        const int flags = s_desc[j & 3].flags;
-        if (!(flags & 1)) {    // the stream has ended: tell the FFT warps once
-            if (!stop_sent) {
-                stop_sent = true;
-                const uint32_t b = rs & 1u, ph = (rs >> 1) & 1u;
-                if (gtid == 0) {
-                    mbar_wait(&sb_empty[b], ph ^ 1u);
-                    s_go[b] = 0;
-                    mbar_arrive(&sb_full[b]);
-                }
-                ++rs;
-            }
-            return;
-        }
-        if (flags & 2) return;   // silent tile: the FFT warps never see it
-        const ClipCtx* const c = &s_ctx[s_desc[j & 3].slot];
-        const int tile_ = s_desc[j & 3].tile;
-        const uint32_t b = rs & 1u, ph = (rs >> 1) & 1u;
-        float* const sbuf = sb + b * p.ns;
-        mbar_wait(&sb_empty[b], ph ^ 1u);                  // every FFT warp has pulled its frame of the tile before
-        if (stage_gather(c, tile_, sbuf)) group_bar();    // only tiles that touch a clip edge, and augmented clips
-        if (gtid == 0) {
-            s_go[b] = 1;
-#if LM_TIMING
-            LM_TR(rs, 0);
-#endif
-            stage_bulk(c, tile_, sbuf, &sb_full[b]);
-        }
-        ++rs;
-    };
-
-    // ---- prologue: items 0-2 scheduled, items 0 and 1 staged ----------------------------------------------
-    if (gtid == 0) {
-        load_clip(p, static_cast<int>(blockIdx.x), &s_ctx[0], NFFT);   // the grid never exceeds the number of (virtual) clips
-        sc_tile = s_ctx[0].t_begin; sc_end = s_ctx[0].t_end;
-        sched(0); sched(1); sched(2);
-    }
-    group_bar();
-    stage_item(0);
-    stage_item(1);
-
-    uint32_t rm = 0;                       // ring items consumed by the mel phase so far
-    bool fb_ready = false;                 // this thread has seen the filterbank copy complete
-    s_stat[gtid] = make_longlong2(0, 0);    // this thread's running (sum, sum of squares) of the clip's dB values, fixed point
-
-#if LM_TIMING
-    long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long t_last = clock64();
-#endif
-#pragma unroll 1
-    for (int it = 0;; ++it) {
-        const ItemDesc d = s_desc[it & 3];
-        if (!(d.flags & 1)) break;
-        if (gtid == 0) sched(it + 3);
-        stage_item(it + 2);
-        LM_T(0);
-
-        const ClipCtx* __restrict__ cx = &s_ctx[d.slot];
-        const int clip = cx->clip;
-        const int tf = d.tile * TILE_F;                // first frame of the tile
-        const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
-        float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
-        float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
-        float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
-        const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
-        float ssum = 0.0f, qsum = 0.0f;   // fp32 over this item's values, fixed point across items
-
-        if (__builtin_expect((d.flags & 2) != 0, 0)) {
-            // ---- silent tile: every feature is the floor (or a mask's 0) ----------------------------------------
-            for (int idx = gtid; idx < n_mels * TILE_F; idx += kGroupThreads) {
-                const int m = idx / TILE_F, f = idx - m * TILE_F, tt = tf + f;
-                if (f < nf) {
-                    const float v = ((m >= cf0 && m < cf1) || (tt >= ct0 && tt < ct1)) ? 0.0f : p.floor_db;
-                    const int o = m * frames + tt;
-                    out[o] = v;
-                    if (EXTRA_OUT) {
-                        if (odb) odb[o] = v;
-                        if (omp) omp[o] = 0.0f;
-                    }
-                    ssum += v;
-                    qsum = fmaf(v, v, qsum);
-                }
-            }
-        } else {
-            // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
-            const uint32_t b = rm & 1u, ph = (rm >> 1) & 1u;
-            ++rm;
-            if (!fb_ready) { mbar_wait(mbar_fb, 0); fb_ready = true; }
-            mbar_wait(&rows_full[b], ph);              // all power rows of the tile are in shared memory
-            LM_T(1);
-#if LM_TIMING
-            if (gtid == 32) LM_TR(rm - 1, 5);
-#endif
-            const float* const rowsb = rows + b * kRowSet;
-            const int lane = lane_, gw = gwarp_;
+        // ---- mel phase: tensor cores, filterbank-stationary, up to kTileSlots 8-mel tiles per warp -------------
+        if (!fb_ready) { mbar_wait(mbar_fb, 0); fb_ready = true; }
+        {
+            const int lane = launder(lane_), gw = launder(gwarp_);
             const int g = lane >> 2, tg = lane & 3;
+            const int nf = (frames - tf) < TILE_F ? (frames - tf) : TILE_F;
+            const ClipCtx* __restrict__ cx = &s_ctx[ord & 1];
+            float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+            float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
+            float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
+            const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
+            float ssum = 0.0f, qsum = 0.0f;   // fp32 over this item's (at most 4 NB kTileSlots) values, fp64 across items
 #pragma unroll 1
             for (int slot = 0; slot < kTileSlots; ++slot) {
                 const int mt = s_tab->warp_tile[gw][slot];
-#ifdef LM_NOMEL
-                break;
-#endif
-                if (mt < 0) break;
+                if (mt < 0 || LM_EXP == 1) break;
                 const int kb = s_tab->kb[mt], ndk = s_tab->ndk[mt];
                 const float4* __restrict__ wp = s_melw + static_cast<size_t>(s_tab->off[mt]) * 64 + lane;
-                // B operand: frame n = g of column block nb lives in row (8 nb + g) / FPW
+                // B operand: frame n = g of column block nb lives in warp row (8 nb + g) / FPW
                 // (+ kPbOff for the odd frame); this lane reads bins kb + 16 d + 4 tg .. +3 of it
                 const float* rp[G::NB];
                 float acc_h[G::NB][4], acc_l[G::NB][4];   // products with the head / the residual of the power
 #pragma unroll
                 for (int nb = 0; nb < G::NB; ++nb) {
                     const int f = 8 * nb + g;
-                    rp[nb] = rowsb + (f / G::FPW) * kRowFloats + (f % G::FPW) * kPbOff + kb + 4 * tg;
+                    rp[nb] = rows + (f / G::FPW) * kRowFloats + (f % G::FPW) * kPbOff + kb + 4 * tg;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { acc_h[nb][q] = 0.f; acc_l[nb][q] = 0.f; }
                 }
 #pragma unroll 2
-                for (int dk = 0; dk < ndk; ++dk) {
+                for (int d = 0; d < ndk; ++d) {
                     // A operand rows 0-7: TF32 head of fb[., mel g], rows 8-15: its residual; one LDS.128 is one
                     // k-step's fragment.  k-step 1: logical k = tg -> bin 4tg, k = tg+4 -> bin 4tg+1; k-step 2: bins 4tg+2, 4tg+3
-                    const float4 w1 = wp[64 * dk], w2 = wp[64 * dk + 32];
+                    const float4 w1 = wp[64 * d], w2 = wp[64 * d + 32];
 #pragma unroll
                     for (int nb = 0; nb < G::NB; ++nb) {
-                        const float4 pv = *reinterpret_cast<const float4*>(rp[nb] + 16 * dk);
+                        const float4 pv = *reinterpret_cast<const float4*>(rp[nb] + 16 * d);
                         const uint32_t p0 = tf32_hi(pv.x), p1 = tf32_hi(pv.y), p2 = tf32_hi(pv.z), p3 = tf32_hi(pv.w);
                         const lm_f2 r01 = lm_sub2(lm_pack(pv.x, pv.y), lm_pack(__uint_as_float(p0), __uint_as_float(p1)));
                         const lm_f2 r23 = lm_sub2(lm_pack(pv.z, pv.w), lm_pack(__uint_as_float(p2), __uint_as_float(p3)));
@@ -967,57 +947,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                     qsum = fmaf(u0, u0, fmaf(u1, u1, qsum));
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&rows_empty[b]);   // this warp is done with the rows: the FFT warps may reuse them
+            stat_add(&s_stat[tid], ssum, qsum);
         }
-        stat_add(&s_stat[gtid], ssum, qsum);
-        LM_T(2);
-#if LM_TIMING
-        if (gtid == 32) LM_TR(rm - 1, 6);
-#endif
 
+        }   // not silent
+        LM_T(5);   // mel phase
+        // ---- gather part of item it+1 (its TMA part is already in flight) -----------------------------
+        const bool has1 = !wrap || (s_ctx[ord1 & 1].clip >= 0);   // written before (B) by thread 0
+        if (wrap && has1) tile1 = s_ctx[ord1 & 1].t_begin;
+        if (has1) {
+            if (stage_gather(&s_ctx[ord1 & 1], tile1)) group_bar(group);   // (C) only for tiles that touch a clip edge
+        }
+
+        LM_T(6);   // gather + barrier C
         // ---- per-clip normalisation --------------------------------------------------------------------
-        if ((d.flags & 4) && p.normalize) {
-            long long s_acc = s_stat[gtid].x, q_acc = s_stat[gtid].y;
+        if (wrap) {
+            if (p.normalize) {
+                float* __restrict__ out = p.out_norm + static_cast<size_t>(clip) * clip_elems;
+                long long s_acc = s_stat[tid].x, q_acc = s_stat[tid].y;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
-                q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
-            }
-            if (lane_ == 0) { red[gwarp_] = s_acc; red[kGroupWarps + gwarp_] = q_acc; }
-            group_bar();   // also orders every thread's dB stores before the re-read below
-            if (gtid == 0) {
-                long long si = 0, qi = 0;
-                for (int w = 0; w < kGroupWarps; ++w) { si += red[w]; qi += red[kGroupWarps + w]; }
-                bool last = true;
-                if (p.split > 1) {
-                    // this chunk's sums join the clip's; the CTA whose arrival completes the clip normalises it.
-                    // The fence makes the CTA's dB stores (ordered before it by the barrier above) visible GPU-wide
-                    // before the arrival counter moves.
-                    atomicAdd(p.clip_stats + 2 * clip, static_cast<unsigned long long>(si));
-                    atomicAdd(p.clip_stats + 2 * clip + 1, static_cast<unsigned long long>(qi));
-                    __threadfence();
-                    last = atomicAdd(p.clip_cnt + clip, 1) == p.split - 1;
-                    if (last) {
-                        __threadfence();
-                        si = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip));
-                        qi = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip + 1));
-                        p.clip_stats[2 * clip] = 0ull;       // nobody else touches this clip's scratch any more
-                        p.clip_stats[2 * clip + 1] = 0ull;
-                        p.clip_cnt[clip] = 0;
-                    }
+                for (int o = 16; o > 0; o >>= 1) {
+                    s_acc += __shfl_xor_sync(0xffffffffu, s_acc, o);
+                    q_acc += __shfl_xor_sync(0xffffffffu, q_acc, o);
                 }
-                const double s = static_cast<double>(si) * (1.0 / kStatScaleS), q = static_cast<double>(qi) * (1.0 / kStatScaleQ);
-                const double n = static_cast<double>(clip_elems);
-                const double mean = s / n;
-                double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
-                if (!(var > 0.0)) var = 0.0;
-                bcast[0] = static_cast<float>(mean);
-                bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
-                bcast[2] = last ? 1.0f : 0.0f;
-            }
-            group_bar();
-            if (bcast[2] != 0.0f) {
+                if (lane_ == 0) { red[gwarp_] = s_acc; red[kGroupWarps + gwarp_] = q_acc; }
+                group_bar(group);   // also orders every thread's dB stores before the re-read below
+                if (gtid == 0) {
+                    long long si = 0, qi = 0;
+                    for (int w = 0; w < kGroupWarps; ++w) { si += red[w]; qi += red[kGroupWarps + w]; }
+                    bool last = true;
+                    if (p.split > 1) {
+                        // this chunk's sums join the clip's; the group whose arrival completes the clip normalises it.
+                        // The fence makes the group's dB stores (ordered before it by the barrier above) visible GPU-wide
+                        // before the arrival counter moves.
+                        atomicAdd(p.clip_stats + 2 * clip, static_cast<unsigned long long>(si));
+                        atomicAdd(p.clip_stats + 2 * clip + 1, static_cast<unsigned long long>(qi));
+                        __threadfence();
+                        last = atomicAdd(p.clip_cnt + clip, 1) == p.split - 1;
+                        if (last) {
+                            __threadfence();
+                            si = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip));
+                            qi = static_cast<long long>(__ldcg(p.clip_stats + 2 * clip + 1));
+                            p.clip_stats[2 * clip] = 0ull;       // nobody else touches this clip's scratch any more
+                            p.clip_stats[2 * clip + 1] = 0ull;
+                            p.clip_cnt[clip] = 0;
+                        }
+                    }
+                    const double s = static_cast<double>(si) * (1.0 / kStatScaleS), q = static_cast<double>(qi) * (1.0 / kStatScaleQ);
+                    const double n = static_cast<double>(clip_elems);
+                    const double mean = s / n;
+                    double var = (q - s * mean) / (n - 1.0);   // unbiased, as torch.std
+                    if (!(var > 0.0)) var = 0.0;
+                    bcast[0] = static_cast<float>(mean);
+                    bcast[1] = static_cast<float>(sqrt(var)) + p.norm_eps;
+                    bcast[2] = last ? 1.0f : 0.0f;
+                }
+                group_bar(group);
+                if (bcast[2] != 0.0f) {
                 const float mean = bcast[0], inv = 1.0f / bcast[1];
                 float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
                 const int n4 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0 ? static_cast<int>(clip_elems >> 2) : 0;
@@ -1049,26 +1035,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 }
                 for (int i = (n4 << 2) + gtid; i < static_cast<int>(clip_elems); i += kGroupThreads)
                     out[i] = (__ldcg(out + i) - mean) * inv;
-            }   // this CTA finishes the clip
+                }   // this group finishes the clip
+                group_bar(group);   // bcast is rewritten at the next clip end
+            }
+            if (!has1) break;
+            s_stat[tid] = make_longlong2(0, 0);
+            clip = s_ctx[ord1 & 1].clip;
+            tile = tile1;
+            t_end = s_ctx[ord1 & 1].t_end;
+            ++ord;
+        } else {
+            ++tile;
         }
-        if (d.flags & 4) s_stat[gtid] = make_longlong2(0, 0);
-        LM_T(4);
-        group_bar();   // publishes the descriptor scheduled in this iteration; bcast / red are rewritten at the next clip end
-        LM_T(5);
-#if LM_TIMING
-        if (gtid == 32) LM_TR(rm - 1, 7);
-#endif
+        LM_T(7);   // normalisation
     }
-#if LM_TIMING
-    LM_T(5);
-    if (lane_ == 0) {
-        long long* o = g_timing + (static_cast<size_t>(blockIdx.x) * kWarps + (tid >> 5)) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = t_acc[i];
-    }
-#endif
     if (!fb_ready) mbar_wait(mbar_fb, 0);   // (all tiles silent) never leave a bulk copy in flight behind an exiting CTA
-    // the last CTA to finish leaves the launch's counters at zero for the next launch that uses this slot
+    // the last group to finish leaves the launch's counters at zero for the next launch that uses this slot
     if (gtid == 0) {
         const int active = n_virtual < nv ? n_virtual : nv;
         __threadfence();
@@ -1077,6 +1059,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             p.work_counter[1] = 0;
         }
     }
+#if LM_TIMING
+    if (lane_ == 0) {
+        long long* o = g_timing + (static_cast<size_t>(blockIdx.x) * kWarps + (tid >> 5)) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = t_acc[i];
+    }
+#endif
 }
 
 }  // namespace lm

@@ -158,6 +158,33 @@ class LogMelPlan:
                                         1 if normalize else 0, C.c_void_p(s.cuda_stream)))
         return out
 
+    def forward_pcm16(self, pcm: torch.Tensor, offset: torch.Tensor, length: torch.Tensor,
+                      aug: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                      normalize: bool = True, out: Optional[torch.Tensor] = None,
+                      stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """`forward` on packed int16 samples (the ICBHI wav sample format; R/src/data/preprocessing.py:55-68 is
+        torchaudio.load, i.e. x / 32768): one kernel, 2 bytes per sample across HBM, bit-identical to decoding
+        first.  Clip starts that are multiples of 8 samples take the bulk-copy staging path."""
+        B = int(offset.numel())
+        for name, t, dt in (("pcm", pcm, torch.int16), ("offset", offset, torch.int64), ("length", length, torch.int32)):
+            if t.device != self.device or t.dtype != dt or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
+        if out is None:
+            out = torch.empty(self.out_shape(B), dtype=torch.float32, device=self.device)
+        elif (out.device != self.device or out.dtype != torch.float32 or not out.is_contiguous()
+              or out.numel() != B * self.n_mels * self.frames):
+            raise ValueError(f"out must be contiguous fp32 [B,1,n_mels,frames] on {self.device}")
+        if aug is not None and (aug.device != self.device or aug.numel() * aug.element_size() != 40 * B):
+            raise ValueError("aug must hold B lm_aug records (40 bytes each) on the plan's device")
+        if noise is not None and (noise.device != self.device or noise.dtype != torch.float32
+                                  or noise.numel() != B * self.target_length or not noise.is_contiguous()):
+            raise ValueError("noise must be contiguous fp32 [B, target_length] on the plan's device")
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        _lib.check(self._lib.lm_forward_pcm16(self._h, pcm.data_ptr(), offset.data_ptr(), length.data_ptr(), B,
+                                              _ptr(aug), _ptr(noise), out.data_ptr(), 1 if normalize else 0,
+                                              C.c_void_p(s.cuda_stream)))
+        return out
+
     def forward_gather(self, wave: torch.Tensor, offset: torch.Tensor, length: torch.Tensor, out_slice_ptr: int,
                        peer_slice_ptrs=(), mc_slice_ptr: int = 0, aug: Optional[torch.Tensor] = None,
                        noise: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> None:

@@ -114,7 +114,7 @@ int lm_plan_info(const lm_plan* plan, lm_info* info);
  * 0 = automatic, 1 = off, k = at most k tile ranges per clip), "host_chunk_clips", "stagger_ns". */
 int lm_plan_set(lm_plan* plan, const char* key, int value);
 /* Number of kernels this plan has launched since creation (lm_forward: 1 per call,
- * lm_forward_host: 1 per chunk, lm_forward_host_pcm16: 2 per chunk). */
+ * lm_forward_host / lm_forward_host_pcm16: 1 per chunk). */
 int64_t lm_plan_launch_count(const lm_plan* plan);
 
 /*
@@ -130,6 +130,18 @@ int64_t lm_plan_launch_count(const lm_plan* plan);
 int lm_forward(lm_plan* plan, const float* wave, const int64_t* offset, const int32_t* length,
                int32_t B, const lm_aug* aug, const float* noise, float* out_norm, float* out_db,
                float* out_melpow, int32_t normalize, void* cuda_stream);
+
+/*
+ * lm_forward on 16-bit PCM, the sample format of the ICBHI wav files (R/src/data/preprocessing.py:55-68:
+ * torchaudio.load decodes them to x / 32768 before anything else happens).  `pcm` is a DEVICE pointer to packed
+ * int16 samples; offset / length count samples.  The kernel stages the raw samples (2 bytes each across HBM) and
+ * expands them in shared memory: results are bit-identical to lm_pcm16_decode followed by lm_forward, without the
+ * decode kernel and the fp32 copy of the waveforms.  Clips whose first staged sample is 16-byte aligned
+ * (offset + centre-crop start a multiple of 8 samples) take the bulk-copy path, others the gather path.
+ */
+int lm_forward_pcm16(lm_plan* plan, const int16_t* pcm, const int64_t* offset, const int32_t* length,
+                     int32_t B, const lm_aug* aug, const float* noise, float* out_norm, int32_t normalize,
+                     void* cuda_stream);
 
 /*
  * lm_forward fused with the feature all-gather of the multi-GPU layout (the reference
@@ -194,8 +206,8 @@ int lm_pcm16_decode(const int16_t* in, float* out, int64_t n, void* cuda_stream)
 /*
  * lm_forward_host for clips that are still 16-bit PCM (the sample format of the ICBHI wav files and of
  * every temp wav the analyzers write): the int16 samples cross PCIe -- half the bytes of the fp32 call --
- * and are decoded on the device (lm_pcm16_decode) in front of the log-mel kernel.  offset/length count
- * samples.  Features are bit-identical to lm_forward_host on pcm[i] / 32768.
+ * and are expanded inside the log-mel kernel's staging (lm_forward_pcm16): one kernel per chunk.  offset/length
+ * count samples.  Features are bit-identical to lm_forward_host on pcm[i] / 32768.
  */
 int lm_forward_host_pcm16(lm_plan* plan, const int16_t* pcm, int64_t total_samples, const int64_t* offset,
                           const int32_t* length, int32_t B, const lm_aug* aug, const float* noise, float* out,

@@ -319,6 +319,57 @@ def test_pcm16_host_path_matches_decoded_floats(A):
     assert np.abs(out_h[0, 0].numpy() - ref).max() < NORM_ATOL
 
 
+@pytest.mark.parametrize("n_fft,hop", [(2048, 512), (1024, 256)])
+def test_fused_pcm16_kernel_is_bit_identical_to_decode_then_forward(A, n_fft, hop):
+    """lm_forward_pcm16 (raw 16-bit samples staged by the bulk copy and expanded in shared memory, or converted sample
+    by sample on the gather path) == lm_pcm16_decode + lm_forward, bit for bit: clips that start on 8-sample boundaries
+    (bulk path) and on odd ones (gather path), short / empty / cropped clips, augmented clips (roll, gain, host noise,
+    on-device noise, masks), normalised and dB outputs, and a small batch that is split over the CTAs."""
+    plan = get_plan(A, n_fft, hop)
+    dev = plan.device
+    rs = np.random.RandomState(31)
+    lens = [80000, 80000, 12345, 80001, 0, 99999, 80000, 7, 64000, 80000, 80000, 3000]
+    starts, pos = [], 0
+    for i, n in enumerate(lens):
+        pos = (pos + 7) // 8 * 8 + (0 if i % 3 else 0)   # 16-byte aligned starts ...
+        if i in (3, 6, 10):
+            pos += 3                                        # ... except these: the gather path
+        starts.append(pos)
+        pos += n
+    pcm = torch.from_numpy(rs.randint(-32768, 32768, size=pos + 8).astype(np.int16)).to(dev)
+    offset = torch.tensor(starts, dtype=torch.int64, device=dev)
+    length = torch.tensor(lens, dtype=torch.int32, device=dev)
+    dec = plan.pcm16_decode(pcm)
+    B = len(lens)
+    aug = A.make_aug_array(B)
+    aug["shift"][1], aug["gain"][1] = 4001, 0.5
+    aug["noise_scale"][5], aug["seed"][5] = 0.01, 99
+    aug["noise_scale"][9] = 0.005
+    aug["f0"][2], aug["f1"][2], aug["t0"][2], aug["t1"][2] = 3, 17, 10, 40
+    noise = torch.from_numpy(rs.standard_normal((B, plan.target_length)).astype(np.float32)).to(dev)
+    d_aug = plan.upload_aug(aug)
+    for kw in (dict(), dict(normalize=False), dict(aug=d_aug, noise=noise), dict(aug=d_aug)):
+        want = plan.forward(dec, offset, length, **kw)
+        got = plan.forward_pcm16(pcm, offset, length, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), kw.keys()
+    # small batch: the clips' tiles are dealt to many CTAs; also one launch per clip
+    for i in (0, 3, 8):
+        want = plan.forward(dec, offset[i:i + 1], length[i:i + 1])
+        got = plan.forward_pcm16(pcm, offset[i:i + 1], length[i:i + 1])
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), i
+    # a few hundred full-length clips: several clips per group, dynamic scheduling
+    Bn, T = 600, plan.target_length
+    big = torch.from_numpy(rs.randint(-20000, 20000, size=Bn * T).astype(np.int16)).to(dev)
+    off = torch.arange(Bn, device=dev, dtype=torch.int64) * T
+    ln = torch.full((Bn,), T, device=dev, dtype=torch.int32)
+    want = plan.forward(plan.pcm16_decode(big), off, ln)
+    got = plan.forward_pcm16(big, off, ln)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
 def test_icbhi_sized_ragged_corpus(A):
     """BASELINE configs[2] at full size on one GPU: ~6900 respiratory cycles of lognormal length
     (0.2 .. 16.2 s), packed back to back, pad / centre-crop to 5 s.  Properties that do not

@@ -9,10 +9,58 @@
 #include "../audio_classification_icbhi_b200/csrc/logmel_kernel.cuh"
 using namespace lm;
 
+// NOISE: what the warps beyond the first `nfft_warps` run beside the FFT warps (until the FFT warps are done):
+//   1 LOP3 chains (ALU pipe)   2 LDS.128 stream (shared-memory pipe)   3 HMMA.1688 TF32 chains (tensor pipe)   4 scalar FFMA chains   5 spin on an mbarrier that never completes
+__device__ __forceinline__ void side_stream(int kind, volatile int* stop, const float4* smem4, uint64_t* bar, float* out) {
+    const int lane = threadIdx.x & 31;
+    uint32_t q[8]; float f[8]; float d[4][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { q[i] = threadIdx.x * 77 + i; f[i] = threadIdx.x * 1e-3f + i; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+    float4 acc = make_float4(0, 0, 0, 0);
+    long long n = 0;
+    while (*stop == 0) {
+        ++n;
+        if (kind == 1) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("lop3.b32 %0, %0, %1, 0x9e3779b9, 0x96;" : "+r"(q[i]) : "r"(q[(i + 1) & 7]));
+        } else if (kind == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(smem_u32(smem4 + lane + 32 * ((i + (int)n) & 7))) : "memory");
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        } else if (kind == 3) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mma_tf32(d[i], q[0], q[1], q[2], q[3], q[4], q[5]);
+        } else if (kind == 4) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(0.999f), "f"(1e-3f));
+        } else {
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(0u) : "memory");
+        }
+    }
+    float r = acc.x + acc.y + acc.z + acc.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += f[i] + __uint_as_float(q[i] & 0xff);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r += d[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r + (float)n;
+}
+
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) fftk(const float* __restrict__ g_win, const float2* __restrict__ g_tw,
                                                const float2* __restrict__ g_utw, const float* __restrict__ g_samples,
-                                               float* out, int iters) {
+                                               float* out, int iters, int nfft_warps = 99, int noise = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);                 // 1024
     float2* s_tw = reinterpret_cast<float2*>(s_win + 1024);            // 32 * kTwRows
@@ -25,7 +73,14 @@ __global__ void __launch_bounds__(MAXT, 1) fftk(const float* __restrict__ g_win,
     for (int i = tid; i < 512; i += blockDim.x) s_utw[i] = g_utw[i];
     for (int i = tid; i < 5632; i += blockDim.x) sb[i] = g_samples[i];
     for (int i = tid; i < (int)(blockDim.x / 32) * kRowFloats; i += blockDim.x) rows[i] = 0.f;
+    __shared__ int s_stop, s_done;
+    __shared__ uint64_t s_bar;
+    if (tid == 0) { s_stop = 0; s_done = 0; mbar_init(&s_bar, 1); }
     __syncthreads();
+    if (warp >= nfft_warps) {
+        side_stream(noise, &s_stop, reinterpret_cast<const float4*>(sb), &s_bar, out);
+        return;
+    }
     float* const scr = rows + warp * kRowFloats;
     const int hop = 512;
     float keep = 0.f;
@@ -47,7 +102,7 @@ __global__ void __launch_bounds__(MAXT, 1) fftk(const float* __restrict__ g_win,
             lm_fft32_aos_from2(z);
         }
         float xr[32], xi[32];
-        warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane, 0u, true);
+        warp_cfft1024_part2(z, xr, xi, scr, s_tw, lane);
         const int srcl = (32 - lane) & 31;
         const bool l0 = (lane == 0);
 #pragma unroll
@@ -87,6 +142,7 @@ __global__ void __launch_bounds__(MAXT, 1) fftk(const float* __restrict__ g_win,
         __syncwarp();
     }
     out[blockIdx.x * blockDim.x + tid] = keep;
+    if (lane == 0 && atomicAdd(&s_done, 1) == min(nfft_warps, (int)(blockDim.x >> 5)) - 1) *reinterpret_cast<volatile int*>(&s_stop) = 1;
 }
 
 template <int MAXT> void run(const char* label, const float* win, const float2* tw, const float2* utw, const float* smp, float* out, int sms) {
@@ -125,7 +181,20 @@ int main() {
     cudaMemcpy(d_tw, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(d_utw, utw.data(), 4096, cudaMemcpyHostToDevice);
     printf("frame transform only (window, 2048-point real FFT, 4|X|^2 -> shared-memory row), no barriers; the shipped kernel runs at ~818 cycles per frame per SM all told\n");
     run<512>("128 regs", d_win, d_tw, d_utw, d_smp, d_out, sms);
-    run<384>("168 regs", d_win, d_tw, d_utw, d_smp, d_out, sms);
-    run<256>("255 regs", d_win, d_tw, d_utw, d_smp, d_out, sms);
+    // 8 FFT warps + 8 warps of a side stream: what does a concurrent instruction stream cost the FFT warps?
+    const char* kinds[6] = {"", "LOP3 chains (ALU)", "LDS.128 stream", "HMMA.1688 TF32 chains", "scalar FFMA chains", "mbarrier.try_wait spin"};
+    for (int kind = 1; kind <= 5; ++kind) {
+        const int iters = 2000, nw = 16;
+        const size_t smem = sizeof(float) * 1024 + sizeof(float2) * (32 * kTwRows + 512) + sizeof(float) * (5632 + nw * kRowFloats);
+        cudaFuncSetAttribute(fftk<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fftk<512><<<sms, 512, smem>>>(d_win, d_tw, d_utw, d_smp, d_out, 10, 8, kind);
+        cudaDeviceSynchronize();
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        fftk<512><<<sms, 512, smem>>>(d_win, d_tw, d_utw, d_smp, d_out, iters, 8, kind);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("8 FFT warps + 8 warps of %-24s: %7.1f cycles per frame per SM   %s\n", kinds[kind], ms * 1.965e6 / (double(iters) * 8), cudaGetErrorString(cudaGetLastError()));
+    }
     return 0;
 }
