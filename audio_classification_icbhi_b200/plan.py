@@ -232,7 +232,7 @@ class LogMelPlan:
                      normalize: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host tensors in, host features out; H2D / kernel / D2H are pipelined inside the
         library on plan-owned streams.  Pinned tensors make the copies asynchronous.
-        ``wave`` is fp32 samples or int16 PCM (decoded on the device as x / 32768: half the PCIe bytes)."""
+        ``wave`` is fp32 samples or int16 PCM (expanded to x / 32768 inside the kernel: half the PCIe bytes)."""
         B = int(offset.numel())
         if wave.dtype not in (torch.float32, torch.int16):
             raise ValueError("wave must be fp32 samples or int16 PCM")

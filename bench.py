@@ -605,7 +605,7 @@ def run_b200(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": profiled_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "not HBM-bound: the fp32 FFT runs at ~75 % of the schedulers' dispatch bound, 44 % of the fp32 issue peak (DESIGN.md section 5)"},
+                         "note": "not HBM-bound: 44 % of the fp32 peak; the frame transform alone runs at 432 cycles per frame per SM (85 % FMA), the whole kernel at 818 (DESIGN.md sections 4.3 and 5)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(BATCH * T_LEN * 4 + BATCH * 12),
                     "d2h_bytes_per_step": int(out.numel() * 4), "steps": e2e_steps, "matches_device_path": e2e_ok,
@@ -613,7 +613,7 @@ def run_b200(args) -> None:
             "e2e_pcm16": {"value": pcm_value, "unit": UNIT, "h2d_bytes_per_step": int(BATCH * T_LEN * 2 + BATCH * 12),
                           "d2h_bytes_per_step": int(out.numel() * 4), "steps": e2e_steps,
                           "matches_device_path_on_decoded_samples": pcm_ok,
-                          "api": "lm_forward_host_pcm16: the clips as int16 PCM (wav sample format), decoded on the device; "
+                          "api": "lm_forward_host_pcm16: the clips as int16 PCM (wav sample format), expanded inside the log-mel kernel (one kernel per chunk); "
                                  "not the headline e2e (its input is quantised to 16 bits)"},
             "host_affinity_cpus": numa,
             "gpu_launches": int(launches),
