@@ -16,7 +16,6 @@
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 #include "logmel_kernel.cuh"
-#include "logmel_pipe_kernel.cuh"
 #include "logmel_aux.cuh"
 
 namespace {
@@ -57,8 +56,6 @@ constexpr int kSlots = 3;   // host pipeline depth
 constexpr int kCounters = 1024;      // launches of one plan that may be in flight at once (on any streams); a slot is
                                      // re-zeroed on the launching stream right before its kernel, so launches on ONE
                                      // stream never interfere, and 1024 concurrent streams per plan are out of reach
-constexpr int kPipeCtlSlots = 16;    // control blocks of the pipeline kernel: one per launch in flight (cooperative grids cannot overlap; their memsets can)
-constexpr int kPipeMinClips = 1024;  // below this the grid of the pipeline kernel does not fill (222 producer teams, several clips each)
 constexpr int kMaxSplitClips = 512;  // small-batch mode is used below 2 * SM count clips
 
 struct HostSlot {
@@ -95,12 +92,6 @@ struct lm_plan {
     HostSlot slots[kSlots];
     bool slots_ready = false;
     std::atomic<long long> launches{0};
-    // large-batch pipeline kernel (logmel_pipe_kernel.cuh): power-row rings (stay in L2), per-launch control blocks, mel-warp table
-    float* d_pipe_ring = nullptr;
-    int* d_pipe_ctl = nullptr;
-    lm::PipeMelTable* d_pipe_mel = nullptr;
-    int pipe_ok = 0, pipe_groups = 0, pipe_override = -1;   // override: -1 automatic, 0 never, 1 whenever the call is eligible
-    size_t pipe_smem = 0, pipe_ctl_bytes = 0;
     int* d_counters = nullptr;   // kCounters x {work counter, finished groups} for the kernel's dynamic clip scheduling, one pair per launch in flight
     // small-batch mode scratch, one block per launch in flight: [kMaxSplitClips][2] 64-bit sums, then [kMaxSplitClips] arrival counters
     unsigned char* d_split = nullptr;
@@ -114,7 +105,6 @@ int free_plan(lm_plan* p) {
     if (!p) return LM_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_utw); cudaFree(p->d_melw); cudaFree(p->d_tab); cudaFree(p->d_counters); cudaFree(p->d_split);
-    cudaFree(p->d_pipe_ring); cudaFree(p->d_pipe_ctl); cudaFree(p->d_pipe_mel);
     for (auto& s : p->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         cudaFree(s.d_wave); cudaFree(s.d_pcm); cudaFree(s.d_noise); cudaFree(s.d_out);
@@ -173,23 +163,8 @@ int launch(lm_plan* p, const float* wave, const int64_t* offset, const int32_t* 
         k.clip_cnt = reinterpret_cast<int*>(blk + kMaxSplitClips * 16);
         // zero at plan creation; the group that completes a clip resets its entries
     }
-    const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
-    // Large plain batches: the pipeline kernel (transform SMs feeding mel SMs through L2), bit-identical to the kernel below.
-    if (p->pipe_ok && p->pipe_override != 0 && p->max_ctas == 0 && !pcm16 && !extra && aug == nullptr && noise == nullptr && n_peers == 0 &&
-        mc_out == nullptr && k.split == 1 && p->use_tma && (p->pipe_override == 1 || B >= kPipeMinClips)) {
-        lm::PipeParams pp{};
-        pp.k = k;
-        pp.ring = p->d_pipe_ring;
-        pp.ctl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(p->d_pipe_ctl) + static_cast<size_t>(seq % kPipeCtlSlots) * p->pipe_ctl_bytes);
-        pp.mel_warps = p->d_pipe_mel;
-        pp.n_groups = p->pipe_groups;
-        LM_CUDA(cudaMemsetAsync(pp.ctl, 0, p->pipe_ctl_bytes, stream));
-        void* args[] = {&pp};
-        LM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lm::logmel_pipe_kernel<2048>), dim3(p->pipe_groups * (lm::kPipeFan + 1)),
-                                            dim3(lm::kThreads), args, p->pipe_smem, stream));
-        return LM_OK;
-    }
     const int grid = std::min<int>(B * k.split, cap);
+    const bool extra = (out_db != nullptr) || (out_melpow != nullptr);
     const bool device_noise = (aug != nullptr) && (noise == nullptr);   // clips may ask for Philox noise drawn in the kernel
     if (pcm16) {   // `wave` holds 16-bit samples (lm_forward_pcm16): expanded inside the staging, no decode kernel
         if (extra) return LM_ERR_UNSUPPORTED;
@@ -423,54 +398,6 @@ int lm_plan_create(const lm_config* cfg, int device, lm_plan** out_plan) {
                                      static_cast<int>(p->smem_bytes));
     }
     if (e != cudaSuccess) { free_plan(p); return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
-
-    // ---- pipeline kernel: eligible when every mel tile fits a warp's registers and the padded bands fit the ring rows ----
-    if (p->n_fft == 2048 && n_mt <= lm::kPipeMelWarps + 1 && prop.cooperativeLaunch) {
-        bool ok = true;
-        for (int mt = 0; mt < n_mt; ++mt)
-            ok = ok && tab.kb[mt] + 16 * tab.ndk[mt] <= lm::kPipeRowG;
-        lm::PipeMelTable pm;
-        for (auto& w : pm.warp_tile) { w[0] = -1; w[1] = -1; }
-        if (ok) {
-            // longest tiles first, one per warp, onto the scheduler (warp % 4) with the least tensor work; a 16th tile joins the lightest warp
-            std::vector<int> order(n_mt);
-            for (int i = 0; i < n_mt; ++i) order[i] = i;
-            std::sort(order.begin(), order.end(), [&](int a, int b) { return tab.ndk[a] > tab.ndk[b]; });
-            int load_s[4] = {0, 0, 0, 0}, load_w[lm::kPipeMelWarps] = {0};
-            for (int i = 0; i < n_mt; ++i) {
-                const int mt = order[i];
-                int best = -1;
-                for (int w = 0; w < lm::kPipeMelWarps; ++w) {
-                    const bool free0 = pm.warp_tile[w][0] < 0;
-                    const bool can = (i < lm::kPipeMelWarps) ? free0 : (pm.warp_tile[w][1] < 0);
-                    if (!can) continue;
-                    if (best < 0 || load_s[w & 3] * 64 + load_w[w] < load_s[best & 3] * 64 + load_w[best]) best = w;
-                }
-                if (best < 0) { ok = false; break; }
-                pm.warp_tile[best][pm.warp_tile[best][0] < 0 ? 0 : 1] = mt;
-                load_w[best] += tab.ndk[mt];
-                load_s[best & 3] += tab.ndk[mt] + 2;
-            }
-        }
-        p->pipe_groups = p->sm_count / (lm::kPipeFan + 1);
-        if (ok && p->pipe_groups > 0) {
-            const int n_teams = p->pipe_groups * lm::kPipeRings;
-            const size_t ring_bytes = sizeof(float) * static_cast<size_t>(n_teams) * lm::kPipeSlots * lm::kPipeSlotFloats;
-            p->pipe_ctl_bytes = (lm::pipe_ctl_bytes(n_teams) + 255) & ~size_t(255);
-            p->pipe_smem = std::max(lm::PipeFftSmem::total(p->ns), lm::PipeMelSmem::total(p->n_dk));
-            int max_blocks = 0;
-            ok = p->pipe_smem <= prop.sharedMemPerBlockOptin &&
-                 cudaFuncSetAttribute(lm::logmel_pipe_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->pipe_smem)) == cudaSuccess &&
-                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, lm::logmel_pipe_kernel<2048>, lm::kThreads, p->pipe_smem) == cudaSuccess &&
-                 max_blocks >= 1 &&
-                 cudaMalloc(&p->d_pipe_ring, ring_bytes) == cudaSuccess && cudaMemset(p->d_pipe_ring, 0, ring_bytes) == cudaSuccess &&
-                 cudaMalloc(&p->d_pipe_ctl, p->pipe_ctl_bytes * kPipeCtlSlots) == cudaSuccess &&
-                 cudaMalloc(&p->d_pipe_mel, sizeof(pm)) == cudaSuccess &&
-                 cudaMemcpy(p->d_pipe_mel, &pm, sizeof(pm), cudaMemcpyHostToDevice) == cudaSuccess;
-            cudaGetLastError();
-        }
-        p->pipe_ok = ok ? 1 : 0;
-    }
     *out_plan = p;
     return LM_OK;
 }
@@ -482,18 +409,6 @@ int lm_plan_destroy(lm_plan* plan) { return free_plan(plan); }
 int lm_debug_timing(long long* host_out, int n) {
     cudaDeviceSynchronize();
     return cudaMemcpyFromSymbol(host_out, lm::g_timing, sizeof(long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
-}
-#endif
-
-#if LM_PIPE_DEBUG
-int lm_debug_pipe(int* host_out, int n) {
-    cudaDeviceSynchronize();
-    return cudaMemcpyFromSymbol(host_out, lm::g_pipe_dbg, sizeof(int) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
-}
-int lm_debug_pipe_time(unsigned long long* host_out, int n, int reset) {
-    cudaDeviceSynchronize();
-    if (reset) { static unsigned long long z[160 * 8]; return cudaMemcpyToSymbol(lm::g_pipe_time, z, sizeof(z)) == cudaSuccess ? LM_OK : LM_ERR_CUDA; }
-    return cudaMemcpyFromSymbol(host_out, lm::g_pipe_time, sizeof(unsigned long long) * n) == cudaSuccess ? LM_OK : LM_ERR_CUDA;
 }
 #endif
 
@@ -519,7 +434,6 @@ int lm_plan_set(lm_plan* plan, const char* key, int value) {
     if (!strcmp(key, "host_chunk_clips")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->host_chunk_clips = value; return LM_OK; }
     if (!strcmp(key, "stagger_ns")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->stagger_ns = value; return LM_OK; }
     if (!strcmp(key, "max_ctas")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->max_ctas = value; return LM_OK; }
-    if (!strcmp(key, "pipeline")) { if (value < -1 || value > 1) return LM_ERR_INVALID_ARG; plan->pipe_override = value; return LM_OK; }
     if (!strcmp(key, "split")) { if (value < 0) return LM_ERR_INVALID_ARG; plan->split_override = value; return LM_OK; }
     return LM_ERR_INVALID_ARG;
 }

@@ -883,6 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
             float* __restrict__ odb = (EXTRA_OUT && p.out_db) ? p.out_db + static_cast<size_t>(clip) * clip_elems : nullptr;
             float* __restrict__ omp = (EXTRA_OUT && p.out_melpow) ? p.out_melpow + static_cast<size_t>(clip) * clip_elems : nullptr;
             const int cf0 = cx->f0, cf1 = cx->f1, ct0 = cx->t0, ct1 = cx->t1;
+            float ssum = 0.0f, qsum = 0.0f;   // fp32 over this item's (at most 4 NB kTileSlots) values, fp64 across items
 #pragma unroll 1
             for (int slot = 0; slot < kTileSlots; ++slot) {
                 const int mt = s_tab->warp_tile[gw][slot];
@@ -892,15 +893,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                 // B operand: frame n = g of column block nb lives in warp row (8 nb + g) / FPW
                 // (+ kPbOff for the odd frame); this lane reads bins kb + 16 d + 4 tg .. +3 of it
                 const float* rp[G::NB];
-                // products with the head / the residual of the power, one accumulator chain per k-step of a 16-bin step
-                // (four independent chains per column block: a dependent HMMA.1688 takes ~100 cycles to come back)
-                float acc_h[G::NB][4], acc_l[G::NB][4], acc_h2[G::NB][4], acc_l2[G::NB][4];
+                float acc_h[G::NB][4], acc_l[G::NB][4];   // products with the head / the residual of the power
 #pragma unroll
                 for (int nb = 0; nb < G::NB; ++nb) {
                     const int f = 8 * nb + g;
                     rp[nb] = rows + (f / G::FPW) * kRowFloats + (f % G::FPW) * kPbOff + kb + 4 * tg;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { acc_h[nb][q] = 0.f; acc_l[nb][q] = 0.f; acc_h2[nb][q] = 0.f; acc_l2[nb][q] = 0.f; }
+                    for (int q = 0; q < 4; ++q) { acc_h[nb][q] = 0.f; acc_l[nb][q] = 0.f; }
                 }
 #pragma unroll 2
                 for (int d = 0; d < ndk; ++d) {
@@ -916,15 +915,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                         mma_tf32(acc_h[nb], __float_as_uint(w1.x), __float_as_uint(w1.y), __float_as_uint(w1.z), __float_as_uint(w1.w), p0, p1);
                         mma_tf32(acc_l[nb], __float_as_uint(w1.x), __float_as_uint(w1.y), __float_as_uint(w1.z), __float_as_uint(w1.w),
                                  __float_as_uint(lm_lo(r01)), __float_as_uint(lm_hi(r01)));
-                        mma_tf32(acc_h2[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w), p2, p3);
-                        mma_tf32(acc_l2[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w),
+                        mma_tf32(acc_h[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w), p2, p3);
+                        mma_tf32(acc_l[nb], __float_as_uint(w2.x), __float_as_uint(w2.y), __float_as_uint(w2.z), __float_as_uint(w2.w),
                                  __float_as_uint(lm_lo(r23)), __float_as_uint(lm_hi(r23)));
                     }
                 }
-#pragma unroll
-                for (int nb = 0; nb < G::NB; ++nb)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { acc_h[nb][q] += acc_h2[nb][q]; acc_l[nb][q] += acc_l2[nb][q]; }
                 // epilogue: c0:(head row, frame 2tg) c1:(head, 2tg+1) c2:(residual row, 2tg) c3:(residual, 2tg+1)
                 const int m = mt * 8 + g;
                 const bool ok_m = m < n_mels;
@@ -948,11 +943,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const KParams p) {
                         if (omp) { if (ok0) omp[o] = mp0; if (ok1) omp[o + 1] = mp1; }
                     }
                     const float u0 = ok0 ? v0 : 0.0f, u1 = ok1 ? v1 : 0.0f;
-                    // one fixed-point conversion per (thread, mel tile, column block): the unit the pipeline kernel
-                    // (logmel_pipe_kernel.cuh, one mel tile per warp) shares with this one, so both give the same integers
-                    stat_add(&s_stat[tid], u0 + u1, fmaf(u0, u0, fmaf(u1, u1, 0.0f)));
+                    ssum += u0 + u1;
+                    qsum = fmaf(u0, u0, fmaf(u1, u1, qsum));
                 }
             }
+            stat_add(&s_stat[tid], ssum, qsum);
         }
 
         }   // not silent
