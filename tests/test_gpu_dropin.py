@@ -267,6 +267,27 @@ def test_randomised_geometries_match_oracle():
             db = O.amplitude_to_db(O.mel_power(O.stft_power(w, n_fft, hop), fb))
             ref = O.normalize(db)
             assert np.abs(out[i] - ref).max() < NORM_ATOL, (trial, n_fft, hop, n_mels, T, lens[i])
+        # the same clips as 16-bit PCM: the fused staging (bulk copy + in-place expansion, or the gather path for the
+        # unaligned trials) against decode-then-forward, bit for bit, at this geometry
+        q = np.clip(np.rint(packed * 32768.0), -32768, 32767).astype(np.int16)
+        if trial % 2 == 0:                                  # aligned trials: starts on 8-sample boundaries for the bulk path
+            starts8, pos8 = [], 0
+            for c in clips:
+                starts8.append(pos8)
+                pos8 += (len(c) + 7) // 8 * 8
+            q8 = np.zeros(pos8 + 8, dtype=np.int16)
+            for s8, s4, c in zip(starts8, starts, clips):
+                q8[s8:s8 + len(c)] = q[s4:s4 + len(c)]
+            q, qstarts = q8, starts8
+        else:
+            qstarts = starts
+        d_q = torch.from_numpy(q).to(dev)
+        d_off = torch.tensor(qstarts, dtype=torch.int64, device=dev)
+        d_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+        want = plan.forward(plan.pcm16_decode(d_q), d_off, d_len)
+        got = plan.forward_pcm16(d_q, d_off, d_len)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), ("pcm16", trial, n_fft, hop, n_mels, T)
         plan.close()
 
 
